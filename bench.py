@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- Mpoints/s through the fused view-aggregation forward+backward (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (named in config.workload): the synthetic stress case the metric is quoted on --
+1 M points x 32 views x 128 channels fp32 per GPU, Group-pool variant (scores given), gating on,
+group scaling on, rows gathered through a random permutation (worst-case locality).
+One step = one fused forward + one fused backward over one batch.  Weak scaling: every rank owns an
+independent batch; the only collective is the NCCL all-reduce of the gate-parameter gradients.
+
+value : device-resident throughput (inputs in HBM), CUDA events, max over ranks.
+e2e   : the same step through the host-buffer API (deepviewagg_b200.host_api): pinned host inputs
+        -> H2D -> fwd -> bwd -> D2H of every result, copies inside the timed region.
+roofline : dominant kernel (backward) -- algorithmic bytes / mean launch time vs measured HBM peak.
+cpu_baseline / --impl reference : the oracle port of the reference's PyTorch path timed on the host
+        cores of this box (the reference is pure Python; its own modules cannot travel to the box).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "Mpoints/s through view-agg fwd+bwd"
+UNIT = "Mpoints/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=30)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--points", type=int, default=1_000_000)
+    p.add_argument("--views", type=int, default=32)
+    p.add_argument("--channels", type=int, default=128)
+    p.add_argument("--groups", type=int, default=4)
+    p.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
+    p.add_argument("--idx", default="randperm", choices=["randperm", "arange", "none"])
+    p.add_argument("--counts", default="uniform", choices=["uniform", "ragged"])
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def algorithmic_bytes(N, V, C, G, s):
+    """4-byte row index per view, 8-byte pointer per point, fp32 scores."""
+    fwd = V * (C * s + 4 + 4 * G) + N * (8 + C * s)
+    both = V * (3 * C * s + 8 + 12 * G) + N * (2 * C * s + 16)
+    return fwd, both - fwd
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+_Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+      "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+      "clocks_event_reasons.sw_power_cap")
+_REASONS = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+
+class ClockSampler:
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={_Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                 "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        rows = []
+        try:
+            if self.proc is not None:
+                self.proc.terminate()
+                self.proc.wait(timeout=5)
+            if self.path:
+                rows = [r for r in open(self.path).read().splitlines() if r.strip()]
+                os.unlink(self.path)
+            if not rows:  # region shorter than one sampling period: one immediate query
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={_Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=20)
+                rows = [r for r in out.stdout.splitlines() if r.strip()]
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            f = [c.strip() for c in r.split(",")]
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                for name, val in zip(_REASONS, f[4:8]):
+                    if val == "Active":
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: oracle port of the reference path (pooling.py:285-300 chain + modules.py:518 gather)
+# ---------------------------------------------------------------------------------------------------
+def cpu_problem(n_points, views, C, G, seed=1234):
+    gen = torch.Generator().manual_seed(seed)
+    V = n_points * views
+    return dict(
+        x=torch.randn(V, C, generator=gen), idx=torch.randperm(V, generator=gen),
+        compat=torch.randn(V, G, generator=gen), ptr=torch.arange(0, V + 1, views),
+        gw=torch.ones(1, G), gb=torch.zeros(1, G), gout=torch.randn(n_points, C, generator=gen))
+
+
+def cpu_step(pr, G):
+    from oracle import pooling_oracle as O
+    x = pr["x"].requires_grad_(True)
+    c = pr["compat"].requires_grad_(True)
+    gw = pr["gw"].requires_grad_(True)
+    gb = pr["gb"].requires_grad_(True)
+    out, _ = O.view_attention(x, c, pr["ptr"], G, idx=pr["idx"], gate_weight=gw, gate_bias=gb,
+                              group_scaling=True)
+    torch.autograd.grad(out, [x, c, gw, gb], grad_outputs=pr["gout"])
+
+
+def cpu_pick_size(views, C, G, total_budget_s, n_steps):
+    """Probe at 2000 points, then size the sample so n_steps steps take ~total_budget_s."""
+    probe = 2000
+    pr = cpu_problem(probe, views, C, G)
+    cpu_step(pr, G)
+    t0 = time.perf_counter()
+    cpu_step(pr, G)
+    dt = time.perf_counter() - t0
+    rate = probe / max(dt, 1e-6)                       # points / s
+    n = int(rate * total_budget_s / max(n_steps, 1))
+    return max(2000, min(n, 200_000))
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    C, G, v = args.channels, args.groups, args.views
+    n = cpu_pick_size(v, C, G, total_budget_s=90.0, n_steps=args.steps + args.warmup)
+    pr = cpu_problem(n, v, C, G)
+    for _ in range(args.warmup):
+        cpu_step(pr, G)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(pr, G)
+    dt = time.perf_counter() - t0
+    val = n * args.steps / dt / 1e6
+    sample = f"{n} points x {v} views x {C} ch fp32 per step, fwd+bwd, torch CPU {torch.get_num_threads()} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, 1),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"synthetic stress: {args.points} points x {args.views} views x {args.channels} ch "
+                        f"per GPU, Group-pool variant A (scores given), G={args.groups}, gating, "
+                        f"group_scaling, idx={args.idx}, counts={args.counts}",
+            "points_per_gpu": args.points, "views": args.views, "channels": args.channels,
+            "groups": args.groups, "idx": args.idx, "counts": args.counts, "parallelism": f"dp{world}",
+            "l2": "inputs (>16 GB per step) exceed the 126 MB L2; no explicit flush needed"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from deepviewagg_b200 import _lib
+    from deepviewagg_b200.host_api import ViewAttentionHostPlan
+
+    N, v, C, G = args.points, args.views, args.channels, args.groups
+    tdtype = torch.float32 if args.dtype == "f32" else torch.bfloat16
+    s = 4 if args.dtype == "f32" else 2
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    if args.counts == "uniform":
+        counts = torch.full((N,), v, dtype=torch.long, device=dev)
+    else:  # clamp(Poisson(v), 0, 4v) with 10 % unseen points
+        counts = torch.poisson(torch.full((N,), float(v), device=dev), generator=gen).clamp(0, 4 * v).long()
+        counts[torch.rand(N, device=dev, generator=gen) < 0.1] = 0
+    ptr = torch.cat([torch.zeros(1, dtype=torch.long, device=dev), counts.cumsum(0)])
+    V = int(ptr[-1].item())
+    idx_dtype = None if args.idx == "none" else torch.int32
+    plan = ViewAttentionHostPlan(N, V, V, C, G, dtype=tdtype, idx_dtype=idx_dtype, gating=True,
+                                 group_scaling=True, device=dev)
+    plan.ptr.copy_(ptr)
+    plan.x.copy_(torch.randn(V, C, device=dev, generator=gen).to(tdtype))
+    if args.idx == "randperm":
+        plan.idx.copy_(torch.randperm(V, device=dev, generator=gen).int())
+    elif args.idx == "arange":
+        plan.idx.copy_(torch.arange(V, device=dev).int())
+    plan.compat.copy_(torch.randn(V, G, device=dev, generator=gen))
+    plan.gate[0].fill_(1.0)
+    plan.gate[1].fill_(0.0)
+    plan.gout.copy_(torch.randn(N, C, device=dev, generator=gen).to(tdtype))
+    torch.cuda.synchronize()
+
+    def step():
+        plan.forward_device()
+        plan.backward_device()
+        if dist is not None:  # the path's only exchange: parameter gradients
+            dist.all_reduce(plan.ggate)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    K = args.steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = _lib.launch_count()
+    sampler.start()
+    e0.record()
+    for k in range(K):
+        ev[k][0].record()
+        plan.forward_device()
+        ev[k][1].record()
+        plan.backward_device()
+        ev[k][2].record()
+        if dist is not None:
+            dist.all_reduce(plan.ggate)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    launches = _lib.launch_count() - launches0
+    if dist is not None:
+        dist.barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+    pts = torch.tensor([float(N)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pts, op=dist.ReduceOp.SUM)
+    elapsed_ms = float(t.item())
+    total_points = float(pts.item())
+    value = total_points * K / (elapsed_ms * 1e-3) / 1e6
+
+    fwd_ms = statistics.mean(ev[k][0].elapsed_time(ev[k][1]) for k in range(K))
+    bwd_ms = statistics.mean(ev[k][1].elapsed_time(ev[k][2]) for k in range(K))
+    b_fwd, b_bwd = algorithmic_bytes(N, V, C, G, s)
+    peak, peak_src = hbm_peak()
+    ach_bwd = b_bwd / (bwd_ms * 1e-3) / 1e9
+    ach_fwd = b_fwd / (fwd_ms * 1e-3) / 1e9
+    ach_step = (b_fwd + b_bwd) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "view_attention_bwd_kernel", "achieved": ach_bwd, "peak": peak,
+                "unit": "GB/s", "frac": ach_bwd / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": b_bwd, "ms_per_launch": bwd_ms}
+    extra_roof = {
+        "fwd": {"kernel": "view_attention_fwd_kernel", "achieved": ach_fwd, "frac": ach_fwd / peak,
+                "algorithmic_bytes_per_launch": b_fwd, "ms_per_launch": fwd_ms},
+        "fwd_plus_bwd": {"achieved": ach_step, "frac": ach_step / peak,
+                         "algorithmic_bytes": b_fwd + b_bwd, "ms": fwd_ms + bwd_ms}}
+
+    # ---- e2e: host buffers, copies inside the timed region ---------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, plan, dist, dev, world, N, V)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        n_cpu = cpu_pick_size(v, C, G, total_budget_s=15.0, n_steps=3)
+        pr = cpu_problem(n_cpu, v, C, G)
+        cpu_step(pr, G)
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            cpu_step(pr, G)
+        dt = (time.perf_counter() - t0) / reps
+        cpu_baseline = {"value": n_cpu / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{n_cpu} points x {v} views x {C} ch fp32, fwd+bwd, oracle port of "
+                                  f"pooling.py:285-300 + modules.py:518 on torch CPU ({cores} threads), "
+                                  f"mean of {reps} after 1 warm-up"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": workload_config(args, world), "clocks": clocks, "e2e": e2e,
+            "gpu_launches": int(launches), "roofline": roofline, "roofline_detail": extra_roof,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, plan, dist, dev, world, N, V):
+    """Same step through the host-buffer API. Pinned buffers for the whole batch (x alone is
+    V*C*s bytes); if the host cannot hold them the e2e leg is skipped with a reason."""
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = None
+    need = sum(t.numel() * t.element_size() for t in (plan.x, plan.gx, plan.compat, plan.gcompat,
+                                                      plan.gout, plan.out, plan.ptr))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    if avail is not None and need * local_world * 1.3 > avail:
+        return {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "skipped": f"host RAM: need {need * local_world / 2**30:.0f} GiB pinned, "
+                           f"{avail / 2**30:.0f} GiB available"}
+    ins, outs = plan.host_buffers(pin=True)
+    for k, h in ins.items():           # fill the caller-side buffers with this rank's data
+        h.copy_(getattr(plan, k))
+    torch.cuda.synchronize()
+    steps = max(2, min(args.steps, 3))
+    plan.run_host(ins, outs)            # warm-up (page-locks are already in place)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(steps):
+        h2d, d2h = plan.run_host(ins, outs)
+        if dist is not None:
+            dist.all_reduce(plan.ggate)
+    b.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    val = world * N * steps / (float(ms.item()) * 1e-3) / 1e6
+    return {"value": val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "steps": steps, "ms_per_step": float(ms.item()) / steps,
+            "api": "deepviewagg_b200.host_api.ViewAttentionHostPlan.run_host (pinned host buffers)"}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,370 @@
+// Segmented (CSR) reductions, broadcast and softmax: the building blocks every pool of
+// torch_points3d/modules/multimodal/pooling.py composes (segment_csr at :63,:289,:295,:519,:525,
+// :628,:787,:807,:851; gather_csr :813-841; segment_softmax_csr :758-810).
+//
+// Layout: src [n_items,K] row-major, ptr [n_seg+1] int64.  One thread owns one (segment,
+// column-vector) pair and walks the segment's rows in order -- adjacent threads own adjacent
+// columns, so every row read/write is a coalesced 16-byte-per-lane access, and the reduction
+// order is the sequential order of torch_scatter's CPU kernel (deterministic, first arg-max).
+// These are HBM-bound streaming kernels: bytes = n_items*K*s (read) + n_seg*K*s (write).
+#include "dva_common.cuh"
+
+namespace dva {
+
+template <int RED> struct RedOp;
+template <> struct RedOp<DVA_SUM> { static __device__ __forceinline__ bool better(float a, float b) { return false; } };
+template <> struct RedOp<DVA_MAX> { static __device__ __forceinline__ bool better(float a, float b) { return a > b; } };
+template <> struct RedOp<DVA_MIN> { static __device__ __forceinline__ bool better(float a, float b) { return a < b; } };
+
+// ---- forward -----------------------------------------------------------------------------
+template <typename T, int VEC, int RED>
+__global__ void __launch_bounds__(256)
+segment_csr_fwd_kernel(const T* __restrict__ src, const int64_t* __restrict__ ptr,
+                       T* __restrict__ out, int64_t* __restrict__ arg, int64_t n_seg,
+                       int64_t n_items, int64_t K) {
+  const int64_t KV = K / VEC;
+  const int64_t total = n_seg * KV;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / KV, kv = t - i * KV;
+    const int64_t p0 = ptr[i], p1 = ptr[i + 1];
+    float acc[VEC];
+    int64_t best[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { acc[j] = 0.f; best[j] = n_items; }
+    const T* col = src + kv * VEC;
+    for (int64_t p = p0; p < p1; ++p) {
+      Pack<T, VEC> raw = *reinterpret_cast<const Pack<T, VEC>*>(col + p * K);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const float v = Cvt<T>::to_f(raw.v[j]);
+        if (RED == DVA_SUM || RED == DVA_MEAN) {
+          acc[j] += v;
+        } else {
+          constexpr int R2 = (RED == DVA_MIN) ? DVA_MIN : DVA_MAX;
+          if (p == p0 || RedOp<R2>::better(v, acc[j])) { acc[j] = v; best[j] = p; }
+        }
+      }
+    }
+    if (RED == DVA_MEAN) {
+      const float inv = 1.f / (float)((p1 - p0) > 0 ? (p1 - p0) : 1);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) acc[j] *= inv;
+    }
+    Pack<T, VEC> o;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) o.v[j] = Cvt<T>::from_f(acc[j]);
+    *reinterpret_cast<Pack<T, VEC>*>(out + i * K + kv * VEC) = o;
+    if ((RED == DVA_MAX || RED == DVA_MIN) && arg != nullptr) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) arg[i * K + kv * VEC + j] = best[j];
+    }
+  }
+}
+
+// ---- backward: every row of grad_src is written exactly once (segments partition the rows)
+template <typename T, int VEC, int RED>
+__global__ void __launch_bounds__(256)
+segment_csr_bwd_kernel(const T* __restrict__ gout, const int64_t* __restrict__ ptr,
+                       const int64_t* __restrict__ arg, T* __restrict__ gsrc, int64_t n_seg,
+                       int64_t K) {
+  const int64_t KV = K / VEC;
+  const int64_t total = n_seg * KV;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / KV, kv = t - i * KV;
+    const int64_t p0 = ptr[i], p1 = ptr[i + 1];
+    if (p1 <= p0) continue;
+    Pack<T, VEC> g = *reinterpret_cast<const Pack<T, VEC>*>(gout + i * K + kv * VEC);
+    int64_t a[VEC];
+    if (RED == DVA_MAX || RED == DVA_MIN) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) a[j] = arg[i * K + kv * VEC + j];
+    }
+    if (RED == DVA_MEAN) {
+      const float inv = 1.f / (float)(p1 - p0);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) g.v[j] = Cvt<T>::from_f(Cvt<T>::to_f(g.v[j]) * inv);
+    }
+    for (int64_t p = p0; p < p1; ++p) {
+      Pack<T, VEC> o = g;
+      if (RED == DVA_MAX || RED == DVA_MIN) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) if (a[j] != p) o.v[j] = Cvt<T>::from_f(0.f);
+      }
+      *reinterpret_cast<Pack<T, VEC>*>(gsrc + p * K + kv * VEC) = o;
+    }
+  }
+}
+
+// ---- gather_csr: broadcast segment rows to their items
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+gather_csr_kernel(const T* __restrict__ src, const int64_t* __restrict__ ptr,
+                  T* __restrict__ out, int64_t n_seg, int64_t K) {
+  const int64_t KV = K / VEC;
+  const int64_t total = n_seg * KV;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / KV, kv = t - i * KV;
+    const int64_t p0 = ptr[i], p1 = ptr[i + 1];
+    if (p1 <= p0) continue;
+    const Pack<T, VEC> g = *reinterpret_cast<const Pack<T, VEC>*>(src + i * K + kv * VEC);
+    for (int64_t p = p0; p < p1; ++p)
+      *reinterpret_cast<Pack<T, VEC>*>(out + p * K + kv * VEC) = g;
+  }
+}
+
+// ---- segment softmax (pooling.py:758-810)
+template <typename T>
+__global__ void __launch_bounds__(256)
+segment_softmax_fwd_kernel(const T* __restrict__ src, const int64_t* __restrict__ ptr,
+                           T* __restrict__ out, int64_t n_seg, int64_t K, float eps,
+                           int scaling) {
+  const int64_t total = n_seg * K;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / K, k = t - i * K;
+    const int64_t p0 = ptr[i], p1 = ptr[i + 1];
+    if (p1 <= p0) continue;
+    float m = Cvt<T>::to_f(src[p0 * K + k]);
+    for (int64_t p = p0 + 1; p < p1; ++p) m = fmaxf(m, Cvt<T>::to_f(src[p * K + k]));
+    // reference divides the centred score by sqrt(count) (pooling.py:792-801)
+    const float sq = scaling ? sqrtf((float)(p1 - p0)) : 1.f;
+    float sum = 0.f;
+    for (int64_t p = p0; p < p1; ++p) sum += expf((Cvt<T>::to_f(src[p * K + k]) - m) / sq);
+    const float den = sum + eps;
+    for (int64_t p = p0; p < p1; ++p)
+      out[p * K + k] = Cvt<T>::from_f(expf((Cvt<T>::to_f(src[p * K + k]) - m) / sq) / den);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+segment_softmax_bwd_kernel(const T* __restrict__ out, const T* __restrict__ gout,
+                           const int64_t* __restrict__ ptr, T* __restrict__ gsrc,
+                           int64_t n_seg, int64_t K, int scaling) {
+  const int64_t total = n_seg * K;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / K, k = t - i * K;
+    const int64_t p0 = ptr[i], p1 = ptr[i + 1];
+    if (p1 <= p0) continue;
+    float dot = 0.f;
+    for (int64_t p = p0; p < p1; ++p)
+      dot += Cvt<T>::to_f(out[p * K + k]) * Cvt<T>::to_f(gout[p * K + k]);
+    const float inv = scaling ? rsqrtf((float)(p1 - p0)) : 1.f;
+    for (int64_t p = p0; p < p1; ++p) {
+      const float a = Cvt<T>::to_f(out[p * K + k]);
+      gsrc[p * K + k] = Cvt<T>::from_f(a * (Cvt<T>::to_f(gout[p * K + k]) - dot) * inv);
+    }
+  }
+}
+
+// ---- heuristic pool (pooling.py:129-152): arg over one mapping feature, then row pick
+__global__ void __launch_bounds__(256)
+heuristic_arg_kernel(const float* __restrict__ x_map, int64_t stride, int64_t feat,
+                     const int64_t* __restrict__ ptr, int64_t* __restrict__ arg, int64_t N,
+                     int64_t V, int use_max) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p0 = ptr[i], p1 = ptr[i + 1];
+    int64_t best = V;
+    float bv = 0.f;
+    for (int64_t p = p0; p < p1; ++p) {
+      const float v = x_map[p * stride + feat];
+      if (p == p0 || (use_max ? v > bv : v < bv)) { bv = v; best = p; }
+    }
+    arg[i] = best;
+  }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+pick_rows_kernel(const T* __restrict__ x, const int64_t* __restrict__ arg, T* __restrict__ out,
+                 int64_t N, int64_t V, int64_t C) {
+  const int64_t CV = C / VEC;
+  const int64_t total = N * CV;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / CV, cv = t - i * CV;
+    const int64_t j = arg[i];
+    Pack<T, VEC> o;
+    if (j >= 0 && j < V) {
+      o = *reinterpret_cast<const Pack<T, VEC>*>(x + j * C + cv * VEC);
+    } else {
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) o.v[q] = Cvt<T>::from_f(0.f);
+    }
+    *reinterpret_cast<Pack<T, VEC>*>(out + i * C + cv * VEC) = o;
+  }
+}
+
+// ---- host-side dispatch ---------------------------------------------------------------------
+static inline int grid_for(int64_t total, int threads = 256) {
+  int64_t blocks = (total + threads - 1) / threads;
+  const int64_t cap = (int64_t)kNumSMs * 16;  // 16 resident 256-thread CTAs cover 2048 thr/SM x2
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+template <typename T>
+static int vec_width(int64_t K, const void* a, const void* b) {
+  constexpr int V = Vec16<T>::N;
+  if (K % V == 0 && aligned16(a) && aligned16(b)) return V;
+  return 1;
+}
+
+template <typename T, int VEC>
+static int seg_fwd_launch(const void* src, const int64_t* ptr, void* out, int64_t* arg,
+                          int64_t n_seg, int64_t n_items, int64_t K, int reduce,
+                          cudaStream_t st) {
+  const int grid = grid_for(n_seg * (K / VEC));
+  const T* s = (const T*)src; T* o = (T*)out;
+  switch (reduce) {
+    case DVA_SUM:  segment_csr_fwd_kernel<T, VEC, DVA_SUM><<<grid, 256, 0, st>>>(s, ptr, o, arg, n_seg, n_items, K); break;
+    case DVA_MEAN: segment_csr_fwd_kernel<T, VEC, DVA_MEAN><<<grid, 256, 0, st>>>(s, ptr, o, arg, n_seg, n_items, K); break;
+    case DVA_MAX:  segment_csr_fwd_kernel<T, VEC, DVA_MAX><<<grid, 256, 0, st>>>(s, ptr, o, arg, n_seg, n_items, K); break;
+    case DVA_MIN:  segment_csr_fwd_kernel<T, VEC, DVA_MIN><<<grid, 256, 0, st>>>(s, ptr, o, arg, n_seg, n_items, K); break;
+    default: return fail(DVA_EINVAL, "segment_csr_fwd: unknown reduce");
+  }
+  return check_launch("segment_csr_fwd");
+}
+
+template <typename T, int VEC>
+static int seg_bwd_launch(const void* gout, const int64_t* ptr, const int64_t* arg, void* gsrc,
+                          int64_t n_seg, int64_t K, int reduce, cudaStream_t st) {
+  const int grid = grid_for(n_seg * (K / VEC));
+  const T* g = (const T*)gout; T* o = (T*)gsrc;
+  switch (reduce) {
+    case DVA_SUM:  segment_csr_bwd_kernel<T, VEC, DVA_SUM><<<grid, 256, 0, st>>>(g, ptr, arg, o, n_seg, K); break;
+    case DVA_MEAN: segment_csr_bwd_kernel<T, VEC, DVA_MEAN><<<grid, 256, 0, st>>>(g, ptr, arg, o, n_seg, K); break;
+    case DVA_MAX:  segment_csr_bwd_kernel<T, VEC, DVA_MAX><<<grid, 256, 0, st>>>(g, ptr, arg, o, n_seg, K); break;
+    case DVA_MIN:  segment_csr_bwd_kernel<T, VEC, DVA_MIN><<<grid, 256, 0, st>>>(g, ptr, arg, o, n_seg, K); break;
+    default: return fail(DVA_EINVAL, "segment_csr_bwd: unknown reduce");
+  }
+  return check_launch("segment_csr_bwd");
+}
+
+#define DVA_DISPATCH_DTYPE(dtype, ...)                                        \
+  switch (dtype) {                                                            \
+    case DVA_F32:  { using T = float; __VA_ARGS__; } break;                   \
+    case DVA_BF16: { using T = __nv_bfloat16; __VA_ARGS__; } break;           \
+    case DVA_F16:  { using T = __half; __VA_ARGS__; } break;                  \
+    default: return fail(DVA_EINVAL, "unknown dtype");                        \
+  }
+
+}  // namespace dva
+
+using namespace dva;
+
+extern "C" int dva_segment_csr_fwd(const void* src, const int64_t* ptr, void* out, int64_t* arg,
+                                   int64_t n_seg, int64_t n_items, int64_t K, int reduce,
+                                   int dtype, void* stream) {
+  if (n_seg < 0 || n_items < 0 || K < 0) return fail(DVA_EINVAL, "segment_csr_fwd: negative size");
+  if (n_seg == 0 || K == 0) return DVA_OK;
+  if (!src && n_items > 0) return fail(DVA_EINVAL, "segment_csr_fwd: null src");
+  if (!ptr || !out) return fail(DVA_EINVAL, "segment_csr_fwd: null ptr/out");
+  cudaStream_t st = (cudaStream_t)stream;
+  DVA_DISPATCH_DTYPE(dtype, {
+    if (vec_width<T>(K, src, out) > 1)
+      return seg_fwd_launch<T, Vec16<T>::N>(src, ptr, out, arg, n_seg, n_items, K, reduce, st);
+    return seg_fwd_launch<T, 1>(src, ptr, out, arg, n_seg, n_items, K, reduce, st);
+  });
+  return DVA_OK;
+}
+
+extern "C" int dva_segment_csr_bwd(const void* grad_out, const int64_t* ptr, const int64_t* arg,
+                                   void* grad_src, int64_t n_seg, int64_t n_items, int64_t K,
+                                   int reduce, int dtype, void* stream) {
+  if (n_seg < 0 || n_items < 0 || K < 0) return fail(DVA_EINVAL, "segment_csr_bwd: negative size");
+  if (n_seg == 0 || K == 0 || n_items == 0) return DVA_OK;
+  if (!grad_out || !ptr || !grad_src) return fail(DVA_EINVAL, "segment_csr_bwd: null pointer");
+  if ((reduce == DVA_MAX || reduce == DVA_MIN) && !arg)
+    return fail(DVA_EINVAL, "segment_csr_bwd: max/min need arg");
+  cudaStream_t st = (cudaStream_t)stream;
+  DVA_DISPATCH_DTYPE(dtype, {
+    if (vec_width<T>(K, grad_out, grad_src) > 1)
+      return seg_bwd_launch<T, Vec16<T>::N>(grad_out, ptr, arg, grad_src, n_seg, K, reduce, st);
+    return seg_bwd_launch<T, 1>(grad_out, ptr, arg, grad_src, n_seg, K, reduce, st);
+  });
+  return DVA_OK;
+}
+
+extern "C" int dva_gather_csr(const void* src, const int64_t* ptr, void* out, int64_t n_seg,
+                              int64_t n_items, int64_t K, int dtype, void* stream) {
+  if (n_seg < 0 || n_items < 0 || K < 0) return fail(DVA_EINVAL, "gather_csr: negative size");
+  if (n_seg == 0 || K == 0 || n_items == 0) return DVA_OK;
+  if (!src || !ptr || !out) return fail(DVA_EINVAL, "gather_csr: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  DVA_DISPATCH_DTYPE(dtype, {
+    if (vec_width<T>(K, src, out) > 1) {
+      constexpr int VEC = Vec16<T>::N;
+      gather_csr_kernel<T, VEC><<<grid_for(n_seg * (K / VEC)), 256, 0, st>>>(
+          (const T*)src, ptr, (T*)out, n_seg, K);
+    } else {
+      gather_csr_kernel<T, 1><<<grid_for(n_seg * K), 256, 0, st>>>((const T*)src, ptr, (T*)out,
+                                                                   n_seg, K);
+    }
+    return check_launch("gather_csr");
+  });
+  return DVA_OK;
+}
+
+extern "C" int dva_segment_softmax_csr_fwd(const void* src, const int64_t* ptr, void* out,
+                                           int64_t n_seg, int64_t n_items, int64_t K, float eps,
+                                           int scaling, int dtype, void* stream) {
+  if (n_seg < 0 || n_items < 0 || K < 0) return fail(DVA_EINVAL, "segment_softmax_fwd: negative size");
+  if (n_seg == 0 || K == 0 || n_items == 0) return DVA_OK;
+  if (!src || !ptr || !out) return fail(DVA_EINVAL, "segment_softmax_fwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  DVA_DISPATCH_DTYPE(dtype, {
+    segment_softmax_fwd_kernel<T><<<grid_for(n_seg * K), 256, 0, st>>>(
+        (const T*)src, ptr, (T*)out, n_seg, K, eps, scaling);
+    return check_launch("segment_softmax_fwd");
+  });
+  return DVA_OK;
+}
+
+extern "C" int dva_segment_softmax_csr_bwd(const void* out, const void* grad_out,
+                                           const int64_t* ptr, void* grad_src, int64_t n_seg,
+                                           int64_t n_items, int64_t K, int scaling, int dtype,
+                                           void* stream) {
+  if (n_seg < 0 || n_items < 0 || K < 0) return fail(DVA_EINVAL, "segment_softmax_bwd: negative size");
+  if (n_seg == 0 || K == 0 || n_items == 0) return DVA_OK;
+  if (!out || !grad_out || !ptr || !grad_src) return fail(DVA_EINVAL, "segment_softmax_bwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  DVA_DISPATCH_DTYPE(dtype, {
+    segment_softmax_bwd_kernel<T><<<grid_for(n_seg * K), 256, 0, st>>>(
+        (const T*)out, (const T*)grad_out, ptr, (T*)grad_src, n_seg, K, scaling);
+    return check_launch("segment_softmax_bwd");
+  });
+  return DVA_OK;
+}
+
+extern "C" int dva_heuristic_pool_fwd(const void* x_mod, const float* x_map, int64_t map_stride,
+                                      int64_t feat, const int64_t* ptr, void* out, int64_t* arg,
+                                      int64_t N, int64_t V, int64_t C, int use_max, int dtype,
+                                      void* stream) {
+  if (N < 0 || V < 0 || C < 0 || feat < 0 || feat >= map_stride)
+    return fail(DVA_EINVAL, "heuristic_pool: bad sizes");
+  if (N == 0) return DVA_OK;
+  if (!ptr || !out || !arg || (V > 0 && (!x_mod || !x_map)))
+    return fail(DVA_EINVAL, "heuristic_pool: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  heuristic_arg_kernel<<<grid_for(N), 256, 0, st>>>(x_map, map_stride, feat, ptr, arg, N, V, use_max);
+  int rc = check_launch("heuristic_arg");
+  if (rc) return rc;
+  if (C == 0) return DVA_OK;
+  DVA_DISPATCH_DTYPE(dtype, {
+    if (vec_width<T>(C, x_mod ? x_mod : out, out) > 1) {
+      constexpr int VEC = Vec16<T>::N;
+      pick_rows_kernel<T, VEC><<<grid_for(N * (C / VEC)), 256, 0, st>>>((const T*)x_mod, arg, (T*)out, N, V, C);
+    } else {
+      pick_rows_kernel<T, 1><<<grid_for(N * C), 256, 0, st>>>((const T*)x_mod, arg, (T*)out, N, V, C);
+    }
+    return check_launch("pick_rows");
+  });
+  return DVA_OK;
+}

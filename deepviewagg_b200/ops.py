@@ -1,0 +1,436 @@
+"""Autograd operators over the C ABI (include/dva_b200.h).
+
+Each function mirrors one operator of the reference's multimodal path (same argument meaning,
+same empty-segment / tie / eps semantics) and is backed ONLY by the sm_100a kernels of
+libdva_b200.so: CPU tensors or a missing library raise.  Reference citations are relative to the
+reference repository root.
+"""
+import math
+
+import torch
+
+from . import _lib
+from ._lib import REDUCE_CODES, check, dtype_code, ptr, require_cuda, stream_ptr
+
+
+def _as_2d(src):
+    if src.dim() == 1:
+        return src.contiguous().view(-1, 1)
+    if src.dim() == 2:
+        return src.contiguous()
+    return src.contiguous().view(src.shape[0], -1)
+
+
+def _check_csr(csr_idx, device):
+    if csr_idx.dtype != torch.int64:
+        raise TypeError("csr_idx must be a LongTensor (core/multimodal/csr.py:54)")
+    if csr_idx.dim() != 1 or csr_idx.numel() < 1:
+        raise ValueError("csr_idx must be a 1D pointer tensor of size n_groups + 1")
+    if csr_idx.device != device:
+        raise RuntimeError("csr_idx must live on the device of the features")
+    return csr_idx.contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+# segment_csr  (torch_scatter.segment_csr as used at pooling.py:63,289,295,519,525,628,787,807)
+# --------------------------------------------------------------------------------------------
+class _SegmentCSR(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, csr_idx, reduce):
+        require_cuda(src, csr_idx)
+        lib = _lib.load()
+        code = REDUCE_CODES[reduce]
+        shape = src.shape
+        s2 = _as_2d(src)
+        csr_idx = _check_csr(csr_idx, src.device)
+        n_seg, n_items, K = csr_idx.numel() - 1, s2.shape[0], s2.shape[1]
+        # outputs are allocated in their final shape: returning a view from a custom Function
+        # would forbid the in-place updates the reference applies downstream (Gating,
+        # pooling.py:705-711)
+        out = torch.empty((n_seg,) + tuple(shape[1:]), dtype=src.dtype, device=src.device)
+        arg = None
+        if code in (2, 3):
+            arg = torch.empty((n_seg, K), dtype=torch.int64, device=src.device)
+        with torch.cuda.device(src.device):
+            check(lib.dva_segment_csr_fwd(ptr(s2), ptr(csr_idx), ptr(out), ptr(arg), n_seg, n_items,
+                                          K, code, dtype_code(s2), stream_ptr()), "dva_segment_csr_fwd")
+        ctx.code, ctx.n_items, ctx.in_shape = code, n_items, shape
+        ctx.save_for_backward(csr_idx, arg)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        csr_idx, arg = ctx.saved_tensors
+        lib = _lib.load()
+        g2 = _as_2d(grad_out)
+        n_seg, K = g2.shape
+        gsrc = torch.empty(ctx.in_shape, dtype=g2.dtype, device=g2.device)
+        with torch.cuda.device(g2.device):
+            check(lib.dva_segment_csr_bwd(ptr(g2), ptr(csr_idx), ptr(arg), ptr(gsrc), n_seg,
+                                          ctx.n_items, K, ctx.code, dtype_code(g2), stream_ptr()),
+                  "dva_segment_csr_bwd")
+        return gsrc, None, None
+
+
+def segment_csr(src, indptr, out=None, reduce="sum"):
+    """torch_scatter.segment_csr(src, indptr, out=None, reduce) along dim 0.
+
+    Empty segments reduce to 0 for every mode (pooling.py:870); max/min route the gradient to
+    the first arg-max/min row of the segment.
+    """
+    if out is not None:
+        raise NotImplementedError("segment_csr(out=...) is not used by the reference path")
+    if reduce not in REDUCE_CODES:
+        raise ValueError(f"unknown reduce '{reduce}'")
+    return _SegmentCSR.apply(src, indptr, reduce)
+
+
+def segment_csr_arg(src, indptr, reduce="max"):
+    """(values, first-arg rows) like torch_scatter.segment_max_csr; arg = n_items when empty."""
+    require_cuda(src, indptr)
+    lib = _lib.load()
+    s2 = _as_2d(src)
+    indptr = _check_csr(indptr, src.device)
+    n_seg, n_items, K = indptr.numel() - 1, s2.shape[0], s2.shape[1]
+    out = torch.empty((n_seg, K), dtype=src.dtype, device=src.device)
+    arg = torch.empty((n_seg, K), dtype=torch.int64, device=src.device)
+    with torch.cuda.device(src.device):
+        check(lib.dva_segment_csr_fwd(ptr(s2), ptr(indptr), ptr(out), ptr(arg), n_seg, n_items, K,
+                                      REDUCE_CODES[reduce], dtype_code(s2), stream_ptr()),
+              "dva_segment_csr_fwd")
+    tail = tuple(src.shape[1:])
+    return out.view((n_seg,) + tail), arg.view((n_seg,) + tail)
+
+
+# --------------------------------------------------------------------------------------------
+# gather_csr (pooling.py:813-841)
+# --------------------------------------------------------------------------------------------
+class _GatherCSR(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, csr_idx, n_items):
+        require_cuda(src, csr_idx)
+        lib = _lib.load()
+        s2 = _as_2d(src)
+        csr_idx = _check_csr(csr_idx, src.device)
+        n_seg, K = csr_idx.numel() - 1, s2.shape[1]
+        out = torch.empty((n_items,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+        with torch.cuda.device(src.device):
+            check(lib.dva_gather_csr(ptr(s2), ptr(csr_idx), ptr(out), n_seg, n_items, K,
+                                     dtype_code(s2), stream_ptr()), "dva_gather_csr")
+        ctx.in_shape = src.shape
+        ctx.save_for_backward(csr_idx)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        (csr_idx,) = ctx.saved_tensors
+        lib = _lib.load()
+        g2 = _as_2d(grad_out)
+        n_items, K = g2.shape
+        n_seg = csr_idx.numel() - 1
+        gsrc = torch.empty(ctx.in_shape, dtype=g2.dtype, device=g2.device)
+        with torch.cuda.device(g2.device):
+            check(lib.dva_segment_csr_fwd(ptr(g2), ptr(csr_idx), ptr(gsrc), None, n_seg, n_items, K,
+                                          REDUCE_CODES["sum"], dtype_code(g2), stream_ptr()),
+                  "dva_segment_csr_fwd")
+        return gsrc, None, None
+
+
+def gather_csr(src, csr_idx, n_items=None):
+    """Redistribute segment-level rows to their items (pooling.py:813-841).
+
+    `n_items` avoids the device->host read of csr_idx[-1] when the caller knows V already.
+    """
+    if not torch.is_floating_point(src):
+        raise ValueError("`gather_csr` can only be computed over tensors with floating point data types.")
+    if csr_idx.dim() != 1:
+        raise ValueError("`gather_csr` can only be computed over 1D CSR indices.")
+    if src.dim() > 2:
+        raise NotImplementedError("`gather_csr` can only be computed over 1D or 2D source tensors.")
+    if n_items is None:
+        n_items = int(csr_idx[-1].item())
+    return _GatherCSR.apply(src, csr_idx, n_items)
+
+
+def segment_gather_csr(src, csr_idx, reduce="sum"):
+    """segment_csr then gather_csr (pooling.py:844-856)."""
+    return gather_csr(segment_csr(src, csr_idx, reduce=reduce), csr_idx, n_items=src.shape[0])
+
+
+# --------------------------------------------------------------------------------------------
+# segment_softmax_csr (pooling.py:758-810)
+# --------------------------------------------------------------------------------------------
+class _SegmentSoftmaxCSR(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, csr_idx, eps, scaling):
+        require_cuda(src, csr_idx)
+        lib = _lib.load()
+        s2 = _as_2d(src)
+        csr_idx = _check_csr(csr_idx, src.device)
+        n_seg, n_items, K = csr_idx.numel() - 1, s2.shape[0], s2.shape[1]
+        out = torch.empty(src.shape, dtype=src.dtype, device=src.device)
+        with torch.cuda.device(src.device):
+            check(lib.dva_segment_softmax_csr_fwd(ptr(s2), ptr(csr_idx), ptr(out), n_seg, n_items, K,
+                                                  float(eps), int(bool(scaling)), dtype_code(s2),
+                                                  stream_ptr()), "dva_segment_softmax_csr_fwd")
+        ctx.scaling, ctx.in_shape = bool(scaling), src.shape
+        ctx.save_for_backward(csr_idx, out)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        csr_idx, out = ctx.saved_tensors
+        lib = _lib.load()
+        g2 = _as_2d(grad_out)
+        n_items, K = g2.shape
+        gsrc = torch.empty(ctx.in_shape, dtype=g2.dtype, device=g2.device)
+        with torch.cuda.device(g2.device):
+            check(lib.dva_segment_softmax_csr_bwd(ptr(out), ptr(g2), ptr(csr_idx), ptr(gsrc),
+                                                  csr_idx.numel() - 1, n_items, K, int(ctx.scaling),
+                                                  dtype_code(g2), stream_ptr()),
+                  "dva_segment_softmax_csr_bwd")
+        return gsrc, None, None, None
+
+
+def segment_softmax_csr(src, csr_idx, eps=1e-12, scaling=False):
+    """Equivalent of scatter_softmax for CSR indices (pooling.py:758-810), same signature."""
+    if not torch.is_floating_point(src):
+        raise ValueError("`segment_csr_softmax` can only be computed over tensors with floating point data types.")
+    if csr_idx.dim() != 1:
+        raise ValueError("`segment_csr_softmax` can only be computed over 1D CSR indices.")
+    if src.dim() > 2:
+        raise NotImplementedError("`segment_csr_softmax` can only be computed over 1D or 2D source tensors.")
+    return _SegmentSoftmaxCSR.apply(src, csr_idx, eps, scaling)
+
+
+# --------------------------------------------------------------------------------------------
+# fused view attention (modules.py:518 + pooling.py:285-300 / 515-530)
+# --------------------------------------------------------------------------------------------
+def fused_groups_supported(num_groups):
+    return 1 <= num_groups <= 32 and (num_groups & (num_groups - 1)) == 0
+
+
+class _ViewAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, idx, compat, csr_idx, gate_w, gate_b, num_groups, group_scaling, eps,
+                idx_is_permutation):
+        require_cuda(x, idx, compat, csr_idx, gate_w, gate_b)
+        lib = _lib.load()
+        x = x.contiguous()
+        compat = compat.float().contiguous()
+        csr_idx = _check_csr(csr_idx, x.device)
+        N, V, G = csr_idx.numel() - 1, compat.shape[0], int(num_groups)
+        R, C = x.shape
+        if compat.shape[1] != G:
+            raise ValueError(f"compatibilities must be [V,{G}], got {tuple(compat.shape)}")
+        idx64 = 0
+        if idx is not None:
+            if idx.dtype not in (torch.int32, torch.int64):
+                raise TypeError("idx must be int32 or int64")
+            idx = idx.contiguous()
+            idx64 = int(idx.dtype == torch.int64)
+            if idx.numel() != V:
+                raise ValueError("idx must hold one row id per view")
+        elif R != V:
+            raise ValueError("x must hold one row per view when idx is None")
+        gw = gate_w.detach().float().contiguous().view(-1) if gate_w is not None else None
+        gb = gate_b.detach().float().contiguous().view(-1) if gate_b is not None else None
+        out = torch.empty((N, C), dtype=x.dtype, device=x.device)
+        att = torch.empty((V, G), dtype=torch.float32, device=x.device)
+        seg_max = torch.empty((N, G), dtype=torch.float32, device=x.device)
+        seg_den = torch.empty((N, G), dtype=torch.float32, device=x.device)
+        seg_arg = torch.empty((N, G), dtype=torch.int32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.dva_view_attention_fwd(ptr(x), ptr(idx), idx64, ptr(compat), ptr(csr_idx), ptr(gw),
+                                             ptr(gb), ptr(out), ptr(att), ptr(seg_max), ptr(seg_den),
+                                             ptr(seg_arg), N, V, R, C, G, int(bool(group_scaling)),
+                                             float(eps), dtype_code(x), stream_ptr()),
+                  "dva_view_attention_fwd")
+        ctx.cfg = (N, V, R, C, G, bool(group_scaling), idx64, bool(idx_is_permutation),
+                   gate_w.shape if gate_w is not None else None,
+                   gate_b.shape if gate_b is not None else None,
+                   gate_w.dtype if gate_w is not None else None)
+        ctx.save_for_backward(x, idx, compat, csr_idx, gw, gb, seg_max, seg_den, seg_arg)
+        ctx.mark_non_differentiable(att, seg_max)
+        return out, att, seg_max
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out, _ga, _gm):
+        x, idx, compat, csr_idx, gw, gb, seg_max, seg_den, seg_arg = ctx.saved_tensors
+        N, V, R, C, G, scaling, idx64, is_perm, w_shape, b_shape, w_dtype = ctx.cfg
+        lib = _lib.load()
+        grad_out = grad_out.contiguous()
+        scatter = int(idx is not None and is_perm and R == V)
+        gx_rows = torch.empty((V, C), dtype=x.dtype, device=x.device)
+        gcompat = torch.empty((V, G), dtype=torch.float32, device=x.device)
+        ggate, ws, ws_bytes = None, None, 0
+        if gw is not None:
+            ggate = torch.empty((2, G), dtype=torch.float32, device=x.device)
+            ws_bytes = int(lib.dva_view_attention_bwd_workspace_bytes(G))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.dva_view_attention_bwd(ptr(x), ptr(idx), idx64, ptr(compat), ptr(csr_idx), ptr(gw),
+                                             ptr(gb), ptr(grad_out), ptr(seg_max), ptr(seg_den),
+                                             ptr(seg_arg), ptr(gx_rows), ptr(gcompat), ptr(ggate),
+                                             scatter, N, V, R, C, G, int(scaling), dtype_code(x), ptr(ws),
+                                             ws_bytes, stream_ptr()), "dva_view_attention_bwd")
+        if idx is None or scatter:
+            gx = gx_rows
+        else:  # general (non-injective) gather: accumulate duplicated rows
+            gx = torch.zeros((R, C), dtype=x.dtype, device=x.device).index_add_(0, idx.long(), gx_rows)
+        g_w = ggate[0].view(w_shape).to(w_dtype) if gw is not None else None
+        g_b = ggate[1].view(b_shape).to(w_dtype) if gw is not None else None
+        return gx, None, gcompat, None, g_w, g_b, None, None, None, None
+
+
+def view_attention(x, compat, csr_idx, num_groups, idx=None, gate_weight=None, gate_bias=None,
+                   group_scaling=False, eps=1e-12, idx_is_permutation=False):
+    """Fused gather + group softmax + weighted sum (+ gating).
+
+    Returns (x_pool [N,C], attentions [V,G], seg_max [N,G]) where
+      attentions = segment_softmax_csr(compat, csr_idx, scaling=group_scaling)
+      x_pool     = segment_csr(x[idx] * expand_group_feat(attentions), csr_idx, 'sum')
+                   * expand_group_feat(tanh(relu(w * segment_csr(compat,'max') + b)))   if gating
+    i.e. the chain modules.py:518 -> pooling.py:285-300. `idx` (int32/int64 [V], optional) is the
+    row of `x` feeding each view (e.g. ImageData.view_cat_sorting, image.py:1549-1574).
+    """
+    if not fused_groups_supported(num_groups):
+        raise NotImplementedError("fused view attention needs num_groups to be a power of two <= 32")
+    if (gate_weight is None) != (gate_bias is None):
+        raise ValueError("gate_weight and gate_bias go together")
+    return _ViewAttention.apply(x, idx, compat, csr_idx, gate_weight, gate_bias, num_groups,
+                                group_scaling, eps, idx_is_permutation)
+
+
+# --------------------------------------------------------------------------------------------
+# ragged Q.K compatibilities (pooling.py:499-512)
+# --------------------------------------------------------------------------------------------
+class _QKScores(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, keys, queries, csr_idx, num_groups, scale):
+        require_cuda(keys, queries, csr_idx)
+        lib = _lib.load()
+        k32, q32 = keys.float().contiguous(), queries.float().contiguous()
+        csr_idx = _check_csr(csr_idx, keys.device)
+        N, V, G = csr_idx.numel() - 1, k32.shape[0], int(num_groups)
+        D = k32.shape[1] // G
+        if k32.shape[1] != G * D or q32.shape != (N, G * D):
+            raise ValueError("keys must be [V,G*D] and queries [N,G*D]")
+        compat = torch.empty((V, G), dtype=torch.float32, device=keys.device)
+        with torch.cuda.device(keys.device):
+            check(lib.dva_qk_scores_fwd(ptr(k32), ptr(q32), ptr(csr_idx), ptr(compat), N, V, G, D,
+                                        float(scale), stream_ptr()), "dva_qk_scores_fwd")
+        ctx.cfg = (N, V, G, D, float(scale), keys.dtype, queries.dtype)
+        ctx.save_for_backward(k32, q32, csr_idx)
+        return compat
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gcompat):
+        k32, q32, csr_idx = ctx.saved_tensors
+        N, V, G, D, scale, kd, qd = ctx.cfg
+        lib = _lib.load()
+        gcompat = gcompat.float().contiguous()
+        gk, gq = torch.empty_like(k32), torch.empty_like(q32)
+        with torch.cuda.device(k32.device):
+            check(lib.dva_qk_scores_bwd(ptr(k32), ptr(q32), ptr(csr_idx), ptr(gcompat), ptr(gk), ptr(gq),
+                                        N, V, G, D, scale, stream_ptr()), "dva_qk_scores_bwd")
+        return gk.to(kd), gq.to(qd), None, None, None
+
+
+def qk_scores(keys, queries, csr_idx, num_groups, dim_scaling=True):
+    """compat[v,g] = sum_d K[v,g,d] Q[point(v),g,d] (/ sqrt(D) if dim_scaling), pooling.py:499-512."""
+    D = keys.shape[1] // num_groups
+    scale = 1.0 / math.sqrt(D) if dim_scaling else 1.0
+    return _QKScores.apply(keys, queries, csr_idx, num_groups, scale)
+
+
+# --------------------------------------------------------------------------------------------
+# heuristic pool (pooling.py:129-152)
+# --------------------------------------------------------------------------------------------
+class _HeuristicPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_mod, x_map, csr_idx, feat, use_max):
+        require_cuda(x_mod, x_map, csr_idx)
+        lib = _lib.load()
+        x_mod = x_mod.contiguous()
+        m32 = x_map.float().contiguous()
+        csr_idx = _check_csr(csr_idx, x_mod.device)
+        N, V, C = csr_idx.numel() - 1, x_mod.shape[0], x_mod.shape[1]
+        out = torch.empty((N, C), dtype=x_mod.dtype, device=x_mod.device)
+        arg = torch.empty((N,), dtype=torch.int64, device=x_mod.device)
+        with torch.cuda.device(x_mod.device):
+            check(lib.dva_heuristic_pool_fwd(ptr(x_mod), ptr(m32), m32.shape[1], int(feat), ptr(csr_idx),
+                                             ptr(out), ptr(arg), N, V, C, int(bool(use_max)),
+                                             dtype_code(x_mod), stream_ptr()), "dva_heuristic_pool_fwd")
+        ctx.V = V
+        ctx.save_for_backward(arg)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        (arg,) = ctx.saved_tensors
+        # each point picks a distinct view (or none): a plain row scatter, no accumulation
+        g = torch.zeros((ctx.V + 1, grad_out.shape[1]), dtype=grad_out.dtype, device=grad_out.device)
+        g.index_copy_(0, arg, grad_out.contiguous())
+        return g[:ctx.V], None, None, None, None
+
+
+def heuristic_pool(x_mod, x_map, csr_idx, feat, mode="max"):
+    return _HeuristicPool.apply(x_mod, x_map, csr_idx, feat, mode == "max")
+
+
+# --------------------------------------------------------------------------------------------
+# fused feature-map gather + atomic pool (image.py:1285 + pooling.py:63)
+# --------------------------------------------------------------------------------------------
+class _GatherPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fmap, images, pixels, atomic_ptr, reduce, channels_last):
+        require_cuda(fmap, images, pixels, atomic_ptr)
+        lib = _lib.load()
+        fmap = fmap.contiguous()
+        if channels_last:
+            B, H, W, C = fmap.shape
+        else:
+            B, C, H, W = fmap.shape
+        images = images.long().contiguous()
+        if pixels.dtype not in (torch.int16, torch.int32):
+            pixels = pixels.int()
+        pixels = pixels.contiguous()
+        atomic_ptr = _check_csr(atomic_ptr, fmap.device)
+        Vw, P, code = atomic_ptr.numel() - 1, pixels.shape[0], REDUCE_CODES[reduce]
+        out = torch.empty((Vw, C), dtype=fmap.dtype, device=fmap.device)
+        arg = torch.empty((Vw, C), dtype=torch.int64, device=fmap.device) if code in (2, 3) else None
+        with torch.cuda.device(fmap.device):
+            check(lib.dva_gather_pool_fwd(ptr(fmap), int(channels_last), ptr(images), ptr(pixels),
+                                          int(pixels.dtype == torch.int16), ptr(atomic_ptr), ptr(out),
+                                          ptr(arg), B, C, H, W, Vw, P, code, dtype_code(fmap),
+                                          stream_ptr()), "dva_gather_pool_fwd")
+        ctx.cfg = (B, C, H, W, Vw, P, code, bool(channels_last), fmap.shape, fmap.dtype)
+        ctx.save_for_backward(images, pixels, atomic_ptr, arg)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        images, pixels, atomic_ptr, arg = ctx.saved_tensors
+        B, C, H, W, Vw, P, code, cl, shape, dt = ctx.cfg
+        lib = _lib.load()
+        grad_out = grad_out.contiguous()
+        gf = torch.zeros(shape, dtype=torch.float32, device=grad_out.device)
+        with torch.cuda.device(grad_out.device):
+            check(lib.dva_gather_pool_bwd(ptr(grad_out), int(cl), ptr(images), ptr(pixels),
+                                          int(pixels.dtype == torch.int16), ptr(atomic_ptr), ptr(arg),
+                                          ptr(gf), B, C, H, W, Vw, P, code, dtype_code(grad_out),
+                                          stream_ptr()), "dva_gather_pool_bwd")
+        return gf.to(dt), None, None, None, None, None
+
+
+def gather_pool(fmap, images, pixels, atomic_ptr, reduce="max", channels_last=False):
+    """segment_csr(fmap[(images_per_pixel, :, py, px)], atomic_ptr, reduce) without the [P,C] copy."""
+    return _GatherPool.apply(fmap, images, pixels, atomic_ptr, reduce, channels_last)

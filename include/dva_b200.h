@@ -1,0 +1,206 @@
+/*
+ * dva_b200.h -- C ABI of libdva_b200.so: the B200 (sm_100a) multi-view aggregation hot path.
+ *
+ * Every entry point replaces one operator (or a fused chain of operators) on the reference's
+ * path  ImageMapping gather -> per-point ragged attention over views -> softmax-weighted reduce
+ * (DeepViewAgg, torch_points3d/modules/multimodal + torch_points3d/core/multimodal).  The
+ * "replaces" line of each declaration cites the reference file:line (relative to the reference
+ * repository root) whose behaviour the entry point reproduces.
+ *
+ * Conventions (all entry points)
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - all data pointers are DEVICE pointers owned by the caller (workspace included); the
+ *     library never allocates or frees device memory and keeps no global mutable state.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no internal
+ *     synchronisation, never the legacy default stream unless the caller passes it.
+ *   - row-major contiguous tensors. CSR pointers are int64 (the reference dtype,
+ *     core/multimodal/csr.py:54). Row indices are int32 or int64 (`idx_is_i64`).
+ *   - `dtype` selects the storage type of feature tensors (DVA_F32 / DVA_BF16 / DVA_F16);
+ *     scores, softmax statistics and all accumulation are fp32.
+ *   - return value: 0 = OK; <0 = DVA_E* argument error (nothing was launched);
+ *     >0 = cudaError_t of the failed launch.  dva_last_error() gives a thread-local message.
+ */
+#ifndef DVA_B200_H_
+#define DVA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DVA_ABI_VERSION 1
+
+enum { DVA_OK = 0, DVA_EINVAL = -1, DVA_EALIGN = -2, DVA_EUNSUPPORTED = -3 };
+enum { DVA_F32 = 0, DVA_BF16 = 1, DVA_F16 = 2 };
+/* reduce codes follow BimodalCSRPool._POOLING_MODES order-independent names (pooling.py:36) */
+enum { DVA_SUM = 0, DVA_MEAN = 1, DVA_MAX = 2, DVA_MIN = 3 };
+
+int dva_abi_version(void);
+const char* dva_last_error(void);
+/* number of kernels this library has launched from the calling thread since load
+ * (bench.py reports it as gpu_launches). */
+int64_t dva_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * T1 / P1  segment_csr                      replaces torch_scatter.segment_csr as used at
+ *   pooling.py:63 (BimodalCSRPool), :289,:295,:519,:525 (pools), :628 (DeepSetFeat.f_pool),
+ *   :787,:807 (segment_softmax_csr), :851 (segment_gather_csr); image.py:1767.
+ *   out[i,:] = reduce_{p in [ptr[i],ptr[i+1])} src[p,:];  EMPTY segment -> 0 for every reduce
+ *   (pooling.py:870).  mean divides by max(count,1).  For max/min `arg` (nullable, int64
+ *   [n_seg,K]) receives the FIRST arg-max/min row in segment order, or n_items for empty
+ *   segments (torch_scatter convention); backward routes the gradient to that row only.
+ * ------------------------------------------------------------------------------------------ */
+int dva_segment_csr_fwd(const void* src, const int64_t* ptr, void* out, int64_t* arg,
+                        int64_t n_seg, int64_t n_items, int64_t K, int reduce, int dtype,
+                        void* stream);
+/* grad_src[n_items,K] fully written (zeros where no gradient flows). */
+int dva_segment_csr_bwd(const void* grad_out, const int64_t* ptr, const int64_t* arg,
+                        void* grad_src, int64_t n_seg, int64_t n_items, int64_t K, int reduce,
+                        int dtype, void* stream);
+
+/* P8  gather_csr                            replaces pooling.py:813-841
+ *   out[p,:] = src[i,:] for p in [ptr[i],ptr[i+1]).  Its backward is segment_csr(sum). */
+int dva_gather_csr(const void* src, const int64_t* ptr, void* out, int64_t n_seg,
+                   int64_t n_items, int64_t K, int dtype, void* stream);
+
+/* P7  segment_softmax_csr                   replaces pooling.py:758-810
+ *   m = segment max (0 if empty); z = (src-m)/(sqrt(count) if scaling); e = exp(z);
+ *   out = e / (segment_sum(e) + eps).   src/out [n_items,K]. */
+int dva_segment_softmax_csr_fwd(const void* src, const int64_t* ptr, void* out, int64_t n_seg,
+                                int64_t n_items, int64_t K, float eps, int scaling, int dtype,
+                                void* stream);
+/* grad_src = out * (grad_out - sum_seg(out*grad_out)) / (sqrt(count) if scaling) */
+int dva_segment_softmax_csr_bwd(const void* out, const void* grad_out, const int64_t* ptr,
+                                void* grad_src, int64_t n_seg, int64_t n_items, int64_t K,
+                                int scaling, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * P3 / P4 core: fused CSR-gather + ragged group softmax + weighted sum + gating.
+ *   replaces the chain  modules.py:518 (x_mod[idx_sorting] row gather)  ->
+ *   pooling.py:285-300 (GroupBimodalCSRPool)  /  pooling.py:515-530 (QKVBimodalCSRPool):
+ *     a    = segment_softmax_csr(compat, ptr, scaling=group_scaling)          [V,G]
+ *     y    = segment_csr(x[idx] * expand_group_feat(a, G, C), ptr, 'sum')     [N,C]
+ *     t    = tanh(relu(gate_w * segment_csr(compat, ptr, 'max') + gate_b))    [N,G]  (if gating)
+ *     out  = y * expand_group_feat(t, G, C)
+ *   x      [R,C] feature rows (dtype); idx [V] row of x for view v (nullable: identity, R==V)
+ *   compat [V,G] fp32; ptr [N+1] int64; gate_w/gate_b [G] fp32 (both null: no gating)
+ *   out    [N,C] (dtype)
+ *   saved for backward / save_last taps (all nullable except in training):
+ *     att [V,G] fp32 attention a;  seg_max [N,G] fp32;  seg_den [N,G] fp32 (sum e + eps);
+ *     seg_arg [N,G] int32 = first arg-max view (absolute view id, -1 if empty)
+ *   channel->group map: group_sizes(C,G) of pooling.py:737-755 (first C%G groups one wider).
+ *   G must be a power of two <= 32 (all shipped configs use 4); otherwise DVA_EUNSUPPORTED and
+ *   the host composes the unfused entry points above.
+ * ------------------------------------------------------------------------------------------ */
+int dva_view_attention_fwd(const void* x, const void* idx, int idx_is_i64, const float* compat,
+                           const int64_t* ptr, const float* gate_w, const float* gate_b,
+                           void* out, float* att, float* seg_max, float* seg_den,
+                           int32_t* seg_arg, int64_t N, int64_t V, int64_t R, int64_t C,
+                           int64_t G, int group_scaling, float eps, int dtype, void* stream);
+
+/* Backward of the chain above.
+ *   grad_out [N,C] (dtype) -> grad_x_rows [V,C] (dtype; row v is d/d(x[idx[v]]); when
+ *   scatter_rows!=0 and idx!=null it is written to row idx[v] of a [R,C] buffer instead, which
+ *   requires idx to be injective, as view_cat_sorting is, image.py:1549-1574),
+ *   grad_compat [V,G] fp32 (softmax path + gating arg-max path),
+ *   grad_gate [2,G] fp32 (d gate_w ; d gate_b), nullable when no gating.
+ *   workspace: dva_view_attention_bwd_workspace_bytes(G) bytes (per-block partials). */
+size_t dva_view_attention_bwd_workspace_bytes(int64_t G);
+int dva_view_attention_bwd(const void* x, const void* idx, int idx_is_i64, const float* compat,
+                           const int64_t* ptr, const float* gate_w, const float* gate_b,
+                           const void* grad_out, const float* seg_max, const float* seg_den,
+                           const int32_t* seg_arg, void* grad_x_rows, float* grad_compat,
+                           float* grad_gate, int scatter_rows, int64_t N, int64_t V, int64_t R,
+                           int64_t C, int64_t G, int group_scaling, int dtype, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+/* P4  ragged per-group Q.K scores           replaces pooling.py:499-512
+ *   compat[v,g] = scale * sum_d keys[v,g*D+d] * queries[i(v),g*D+d]   (i(v): point of view v;
+ *   the reference materialises repeat_interleave(queries), pooling.py:500).  fp32 I/O. */
+int dva_qk_scores_fwd(const float* keys, const float* queries, const int64_t* ptr, float* compat,
+                      int64_t N, int64_t V, int64_t G, int64_t D, float scale, void* stream);
+int dva_qk_scores_bwd(const float* keys, const float* queries, const int64_t* ptr,
+                      const float* grad_compat, float* grad_keys, float* grad_queries, int64_t N,
+                      int64_t V, int64_t G, int64_t D, float scale, void* stream);
+
+/* P2  HeuristicBimodalCSRPool               replaces pooling.py:129-152
+ *   j_i = first arg-max/min over the segment of x_map[:,feat]; out[i,:] = x_mod[j_i,:] or 0.
+ *   arg [N] int64 (n_items when empty). */
+int dva_heuristic_pool_fwd(const void* x_mod, const float* x_map, int64_t map_stride,
+                           int64_t feat, const int64_t* ptr, void* out, int64_t* arg, int64_t N,
+                           int64_t V, int64_t C, int use_max, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * I5 + P1  fused feature-map gather + atomic pool
+ *   replaces image.py:1285 (x[(img, ..., py, px)] NCHW advanced-index gather) followed by
+ *   modules.py:497-500 -> pooling.py:63 (BimodalCSRPool over the atomic CSR).
+ *   fmap [B,C,H,W] (channels_last=0) or [B,H,W,C] (channels_last=1), dtype
+ *   img [Vw] int64 image of each view; pix [P,2] (x,y) int16/int32 (pix_is_i16)
+ *   aptr [Vw+1] int64 atomic CSR;  out [Vw,C];  arg [Vw,C] int64 pixel slot (nullable, max/min)
+ * ------------------------------------------------------------------------------------------ */
+int dva_gather_pool_fwd(const void* fmap, int channels_last, const int64_t* img, const void* pix,
+                        int pix_is_i16, const int64_t* aptr, void* out, int64_t* arg,
+                        int64_t B, int64_t C, int64_t H, int64_t W, int64_t Vw, int64_t P,
+                        int reduce, int dtype, void* stream);
+/* grad_fmap must be zero-initialised by the caller; gradients are accumulated with fp32
+ * atomics when dtype==DVA_F32 (pixel reuse across views), see DESIGN.md. */
+int dva_gather_pool_bwd(const void* grad_out, int channels_last, const int64_t* img,
+                        const void* pix, int pix_is_i16, const int64_t* aptr, const int64_t* arg,
+                        float* grad_fmap, int64_t B, int64_t C, int64_t H, int64_t W, int64_t Vw,
+                        int64_t P, int reduce, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Z3  z-buffer visibility from splatting    replaces visibility.py:1073-1195 (CPU/numba oracle)
+ *   splat [m,4] int32 (x_a,x_b,y_a,y_b) already clamped, y relative to the un-cropped image;
+ *   dist [m] fp32.  Point i wins pixel (x,y) iff dist is the smallest, ties -> lowest i
+ *   (strict '<' while iterating ascending, visibility.py:1148-1162) -- realised as one
+ *   64-bit atomicMin on (dist_bits<<32 | i).
+ *   zbuf [W*Hc] uint64 workspace (Hc = H - crop_top - crop_bottom), initialised by the call.
+ *   exact==0: idx_map [W*Hc] int64 (-1 = empty) holds the winning point per pixel.
+ *   exact!=0: idx_map re-rasterised with splat centres only: (int(x_proj), int(y_proj)-crop_top),
+ *             highest seen index wins a shared centre (visibility.py:1168-1187).
+ *   x_proj/y_proj [m] fp64 (numba returns float64, visibility.py:252).
+ * ------------------------------------------------------------------------------------------ */
+int dva_zbuffer_splat(const int32_t* splat, const float* dist, const double* x_proj,
+                      const double* y_proj, unsigned long long* zbuf, int64_t* idx_map,
+                      uint8_t* seen, int64_t m, int64_t W, int64_t H, int64_t crop_top,
+                      int64_t crop_bottom, int exact, void* stream);
+
+/* Z2  splat boxes                           replaces visibility.py:630-704 (equirectangular),
+ *   :761-827 (pinhole).  camera: 0 = s3dis_equirectangular, 1 = pinhole (fx, fy given).
+ *   numba evaluates these expressions in float64 (float32 array x Python float), hence the
+ *   double parameters.  Output splat [m,4] int32 (16-byte aligned), clamped to the (cropped)
+ *   image like the reference; y is relative to the un-cropped image. */
+int dva_splat_boxes(const double* x_proj, const double* y_proj, const float* dist,
+                    int32_t* splat, int64_t m, int64_t W, int64_t H, int64_t crop_top,
+                    int64_t crop_bottom, double voxel, double k_swell, double d_swell, int camera,
+                    double fx, double fy, void* stream);
+
+/* Z1  equirectangular camera projection      replaces visibility.py:150-182 + :509-513 + :395-435
+ *   xyz [n,3] fp32; img_pose [12] fp32 on device = camera position (3) followed by the 3x3
+ *   rotation matrix of pose_to_rotation_matrix (visibility.py:57-90), row-major, computed by the
+ *   host mirror.  Outputs dist [n] fp32, x_proj,y_proj [n] fp64, keep [n] uint8 = in
+ *   (r_min,r_max) and inside the (cropped) field of view (no image mask). */
+int dva_project_equirectangular(const float* xyz, const float* img_pose, float* dist,
+                                double* x_proj, double* y_proj, uint8_t* keep, int64_t n,
+                                int64_t W, int64_t H, int64_t crop_top, int64_t crop_bottom,
+                                float r_min, float r_max, void* stream);
+
+/* C1  CSR pointers from sorted dense ids     replaces csr.py:158-172 + :197-229
+ *   ids [n] int64 sorted ascending, values in [0,num_groups) -> ptr [num_groups+1] int64 with
+ *   empty groups inserted (from_dense + insert_empty_groups, image.py:1787-1793). */
+int dva_csr_pointers_from_sorted(const int64_t* ids, int64_t* ptr, int64_t n, int64_t num_groups,
+                                 void* stream);
+
+/* C1  value index of a group selection       replaces csr.py:235-264 (_index_select_pointers)
+ *   ptr_new [k+1] must already hold the exclusive scan of the selected group sizes;
+ *   val_idx[p] = ptr[sel[i]] + (p - ptr_new[i]) for p in [ptr_new[i], ptr_new[i+1]). */
+int dva_csr_select_values(const int64_t* ptr, const int64_t* sel, const int64_t* ptr_new,
+                          int64_t* val_idx, int64_t k, int64_t n_new_items, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVA_B200_H_ */

@@ -1,0 +1,275 @@
+"""Generate tests/golden/*.npz by EXECUTING THE REFERENCE (oracle; test infrastructure).
+
+Run in the build container only (needs /root/reference):
+    PYTORCH_JIT=0 python -m oracle.make_golden
+The reference's own modules (loaded by file path, oracle/ref_loader.py) are run on seeded inputs;
+inputs, parameters (state_dict), outputs and autograd gradients are committed as small fixtures.
+torch_scatter is the documented-semantics stand-in (oracle/scatter_standin.py) -- stated in the
+fixture metadata.  The GPU box has no /root/reference: tests only read the committed fixtures.
+"""
+import os
+import sys
+
+os.environ.setdefault("PYTORCH_JIT", "0")
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+META = "reference=DeepViewAgg@41543bc; torch_scatter=oracle/scatter_standin.py (documented semantics); torch=%s" % torch.__version__
+
+
+def save(name, **arrays):
+    conv = {}
+    for k, v in arrays.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        conv[k] = np.asarray(v)
+    conv["__meta__"] = np.array(META)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **conv)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def ragged_ptr(gen, n, mean, p_empty=0.15, max_mult=4):
+    counts = torch.poisson(torch.full((n,), float(mean)), generator=gen).clamp(0, max_mult * mean).long()
+    counts[torch.rand(n, generator=gen) < p_empty] = 0
+    return torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)])
+
+
+def sd_arrays(module, prefix="sd/"):
+    return {prefix + k: v.clone() for k, v in module.state_dict().items()}
+
+
+def grads_of(out_scalar, tensors, names, prefix):
+    gs = torch.autograd.grad(out_scalar, tensors, allow_unused=True)
+    return {prefix + n: (g if g is not None else torch.zeros_like(t)) for n, g, t in zip(names, gs, tensors)}
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = ref_loader.load_reference()
+    P = ref.pooling
+
+    # ---- known-answer snippets the reference itself holds (pooling.py:913-921) -----------------
+    src = torch.arange(15).float().view(-1, 1).repeat_interleave(2, dim=1)
+    csr = torch.LongTensor([0, 5, 10, 15])
+    save("kat_softmax", src=src, csr=csr, out=P.segment_softmax_csr(src, csr),
+         out_scaled=P.segment_softmax_csr(src.clone(), csr, scaling=True),
+         empty_mid=P.segment_softmax_csr(torch.tensor([[1.], [2.], [3.]]), torch.LongTensor([0, 2, 2, 3])),
+         gather=P.gather_csr(torch.tensor([[1.], [2.], [3.]]), torch.LongTensor([0, 2, 2, 5])),
+         gating=P.Gating(2)(torch.tensor([[-1., .5], [2., 0.]])),
+         group_sizes_10_4=P.group_sizes(10, 4), group_sizes_512_4=P.group_sizes(512, 4),
+         npow2=np.array([P.nearest_power_of_2(x, 64) for x in (48, 96, 160, 288)]))
+
+    # ---- segment primitives on ragged data (ties included: post-ReLU style zeros) --------------
+    gen = torch.Generator().manual_seed(1234)
+    n = 129
+    ptr = ragged_ptr(gen, n, 5)
+    V = int(ptr[-1])
+    for K, tag in ((7, "k7"), (32, "k32")):
+        x = torch.randn(V, K, generator=gen)
+        x = torch.where(torch.rand(V, K, generator=gen) < 0.3, torch.zeros(()), x).clamp(min=-0.5)
+        arrays = dict(src=x, ptr=ptr)
+        w = torch.randn(n, K, generator=gen)
+        for red in ("sum", "mean", "max", "min"):
+            xr = x.clone().requires_grad_(True)
+            o = P.segment_csr(xr, ptr, reduce=red)
+            arrays[f"out_{red}"] = o
+            arrays[f"grad_{red}"] = torch.autograd.grad((o * w).sum(), xr)[0]
+            arrays[f"seg_gather_{red}"] = P.segment_gather_csr(x, ptr, reduce=red)
+        arrays["w"] = w
+        wv = torch.randn(V, K, generator=gen)
+        for scaling in (False, True):
+            xr = x.clone().requires_grad_(True)
+            o = P.segment_softmax_csr(xr, ptr, scaling=scaling)
+            arrays[f"softmax_{int(scaling)}"] = o
+            arrays[f"softmax_grad_{int(scaling)}"] = torch.autograd.grad((o * wv).sum(), xr)[0]
+        arrays["wv"] = wv
+        sr = torch.randn(n, K, generator=gen).requires_grad_(True)
+        o = P.gather_csr(sr, ptr)
+        arrays["gather_src"] = sr
+        arrays["gather_out"] = o
+        arrays["gather_grad"] = torch.autograd.grad((o * wv).sum(), sr)[0]
+        save(f"segment_ops_{tag}", **arrays)
+
+    # ---- pools -----------------------------------------------------------------------------------
+    def run_group(name, N, mean_v, in_mod, out_mod, G, seed, **kw):
+        gen = torch.Generator().manual_seed(seed)
+        torch.manual_seed(seed)
+        ptr = ragged_ptr(gen, N, mean_v)
+        V = int(ptr[-1])
+        m = P.GroupBimodalCSRPool(in_map=8, in_mod=in_mod, out_mod=out_mod, num_groups=G,
+                                  save_last=True, **kw)
+        with torch.no_grad():  # non-trivial BN affine + gating so that every gradient is exercised
+            for k, p in m.named_parameters():
+                if "batch_norm" in k or k.startswith("G."):
+                    p.add_(0.3 * torch.randn(p.shape, generator=gen))
+        m.train()
+        x_mod = torch.randn(V, in_mod, generator=gen).relu().requires_grad_(True)
+        x_map = torch.rand(V, 8, generator=gen).requires_grad_(True)
+        w = torch.randn(N, m.out_mod, generator=gen)
+        sd0 = sd_arrays(m)
+        out = m(None, x_mod, x_map, ptr)
+        params = dict(m.named_parameters())
+        g = grads_of((out * w).sum(), [x_mod, x_map] + list(params.values()),
+                     ["x_mod", "x_map"] + ["param/" + k for k in params], "grad/")
+        save(name, ptr=ptr, x_mod=x_mod, x_map=x_map, w=w, out=out, last_C=m._last_C, last_A=m._last_A,
+             last_G=m._last_G if m.G else np.zeros(0), kw=np.array(repr(dict(
+                 in_map=8, in_mod=in_mod, out_mod=out_mod, num_groups=G, **kw))), **sd0, **g)
+        # eval-mode forward with the post-step running stats
+        m.eval()
+        with torch.no_grad():
+            out_eval = m(None, x_mod, x_map, ptr)
+        save(name + "_eval", ptr=ptr, x_mod=x_mod, x_map=x_map, out=out_eval, **sd_arrays(m),
+             kw=np.array(repr(dict(in_map=8, in_mod=in_mod, out_mod=out_mod, num_groups=G, **kw))))
+
+    run_group("group_pool_toy", 1000, 4, 8, 8, 4, 11, use_num=True)             # config #0 shape
+    run_group("group_pool_c64", 160, 8, 64, 64, 4, 12, use_num=True)             # S3DIS-like
+    run_group("group_pool_usemod", 200, 6, 24, 32, 4, 13, use_num=True, use_mod=True)
+    run_group("group_pool_g1_nogate", 150, 5, 20, 20, 1, 14, gating=False, group_scaling=False,
+              map_encoder="MLPSetFeat")
+    run_group("group_pool_oddgroups", 150, 5, 10, 10, 4, 15, use_num=True, pool="max_mean",
+              fusion="both")                                                      # group sizes 3,3,2,2
+    run_group("group_pool_minmax", 120, 5, 12, 12, 3, 16, map_encoder="MinMaxDiffSetFeat",
+              use_num=True)                                                       # G=3: unfused path
+
+    def run_qkv(name, N, mean_v, in_main, in_mod, G, D, seed, **kw):
+        gen = torch.Generator().manual_seed(seed)
+        torch.manual_seed(seed)
+        ptr = ragged_ptr(gen, N, mean_v)
+        V = int(ptr[-1])
+        m = P.QKVBimodalCSRPool(in_main=in_main, in_map=8, in_mod=in_mod, num_groups=G, nc_qk=D,
+                                save_last=True, **kw)
+        with torch.no_grad():
+            for k, p in m.named_parameters():
+                if "batch_norm" in k or k.startswith("G."):
+                    p.add_(0.3 * torch.randn(p.shape, generator=gen))
+        m.train()
+        x_main = torch.randn(N, in_main, generator=gen).requires_grad_(True)
+        x_mod = torch.randn(V, in_mod, generator=gen).relu().requires_grad_(True)
+        x_map = torch.rand(V, 8, generator=gen).requires_grad_(True)
+        w = torch.randn(N, m.out_mod, generator=gen)
+        sd0 = sd_arrays(m)
+        out = m(x_main, x_mod, x_map, ptr)
+        params = dict(m.named_parameters())
+        g = grads_of((out * w).sum(), [x_main, x_mod, x_map] + list(params.values()),
+                     ["x_main", "x_mod", "x_map"] + ["param/" + k for k in params], "grad/")
+        save(name, ptr=ptr, x_main=x_main, x_mod=x_mod, x_map=x_map, w=w, out=out, last_C=m._last_C,
+             last_A=m._last_A, last_G=m._last_G if m.G else np.zeros(0),
+             kw=np.array(repr(dict(in_main=in_main, in_map=8, in_mod=in_mod, num_groups=G, nc_qk=D, **kw))),
+             **sd0, **g)
+
+    run_qkv("qkv_pool_base", 300, 6, 10, 32, 4, 8, 21, use_num=True)
+    run_qkv("qkv_pool_modqk", 150, 5, 12, 16, 4, 4, 22, use_num=True, use_mod_q=True, use_mod_k=True,
+            group_scaling=True)
+
+    # ---- BimodalCSRPool / Heuristic / fusion ------------------------------------------------------
+    gen = torch.Generator().manual_seed(31)
+    ptr = ragged_ptr(gen, 200, 4)
+    V = int(ptr[-1])
+    x_mod = torch.randn(V, 24, generator=gen).relu()
+    x_map = torch.rand(V, 8, generator=gen)
+    arrays = dict(ptr=ptr, x_mod=x_mod, x_map=x_map)
+    for mode in ("max", "mean", "min", "sum"):
+        arrays["bimodal_" + mode] = P.BimodalCSRPool(mode=mode)(None, x_mod, None, ptr)
+    for mode in ("max", "min"):
+        for feat in (0, 5):
+            arrays[f"heuristic_{mode}_{feat}"] = P.HeuristicBimodalCSRPool(mode=mode, feat=feat)(
+                None, x_mod, x_map, ptr)
+    a = torch.randn(200, 24, generator=gen)
+    b = torch.randn(200, 24, generator=gen)
+    arrays["fusion_a"], arrays["fusion_b"] = a, b
+    for mode in ref.fusion.BimodalFusion.MODES:
+        arrays["fusion_" + mode] = ref.fusion.BimodalFusion(mode)(a, b)
+    save("simple_pools", **arrays)
+
+    make_integer_golden(ref)
+
+
+def make_integer_golden(ref):
+    """Integer side: lex ops, CSR containers, ImageMapping.from_dense / indexing / batching."""
+    lex, csr_mod, image = ref.lex, ref.csr, ref.image
+    # lex KAT
+    a = torch.LongTensor([2, 0, 2, 1, 0])
+    b = torch.LongTensor([1, 5, 0, 3, 5])
+    u = lex.lexunique(a, b)
+    save("kat_lex", a=a, b=b, argsort=lex.lexargsort(a, b), argunique=lex.lexargunique(a, b),
+         unique_a=u[0], unique_b=u[1])
+
+    gen = torch.Generator().manual_seed(77)
+    n_points, n_items = 500, 4000
+    pid = torch.randint(0, n_points, (n_items,), generator=gen)
+    iid = torch.randint(0, 5, (n_items,), generator=gen)
+    pix = torch.randint(0, 64, (n_items, 2), generator=gen).short()
+    feat = torch.rand(n_items, 3, generator=gen)
+    # remove duplicates of (point, image, px, py) like MapImages does (image.py transform :328)
+    keep = lex.lexargunique(pid, iid, pix[:, 0].long(), pix[:, 1].long())
+    pid, iid, pix, feat = pid[keep], iid[keep], pix[keep], feat[keep]
+    m = image.ImageMapping.from_dense(pid, iid, pix, feat, num_points=n_points + 7)
+    sel = torch.randperm(n_points + 7, generator=gen)[:123]
+    ms = m[sel]
+    down = m.downscale_images(4)
+    save("image_mapping", point_ids=pid, image_ids=iid, pixels=pix, features=feat,
+         num_points=np.array(n_points + 7), pointers=m.pointers, images=m.images,
+         atomic_pointers=m.values[1].pointers, out_pixels=m.pixels, out_features=m.features,
+         sel=sel, sel_pointers=ms.pointers, sel_images=ms.images, sel_atomic_pointers=ms.values[1].pointers,
+         sel_pixels=ms.pixels, sel_features=ms.features,
+         down_atomic_pointers=down.values[1].pointers, down_pixels=down.pixels,
+         fmi_batch=m.feature_map_indexing[0], fmi_h=m.feature_map_indexing[2], fmi_w=m.feature_map_indexing[3])
+
+    # merge re-indexing (image.py:2211-2273) as run after a strided sparse conv (modules.py:232-234)
+    merge_idx = torch.randint(0, 180, (n_points + 7,), generator=gen)
+    merge_idx[:180] = torch.arange(180)  # every output voxel present (image.py:2220)
+    mg = m.select_points(merge_idx, mode="merge")
+    save("image_mapping_merge", merge_idx=merge_idx, pointers=mg.pointers, images=mg.images,
+         atomic_pointers=mg.values[1].pointers, pixels=mg.pixels, features=mg.features)
+
+    # z-buffer + projection + splat from the numba CPU path (visibility.py)
+    vis = ref.visibility
+    gen = torch.Generator().manual_seed(5)
+    n = 8000
+    xyz = (torch.rand(n, 3, generator=gen) - 0.5) * torch.tensor([12., 12., 4.])
+    img_xyz = torch.tensor([0.3, -0.2, 0.1])
+    img_opk = torch.tensor([0.05, -0.1, 0.7])
+    W, H = 512, 256
+    for crop_top, crop_bottom, tag in ((0, 0, "nocrop"), (16, 24, "crop")):
+        idx, dist, xp, yp = vis.camera_projection_cpu(
+            xyz, img_xyz, img_opk=img_opk, img_size=(W, H), crop_top=crop_top, crop_bottom=crop_bottom,
+            r_max=8, r_min=0.5, camera="s3dis_equirectangular")
+        arrays = dict(xyz=xyz, img_xyz=img_xyz, img_opk=img_opk, size=np.array([W, H]),
+                      crop=np.array([crop_top, crop_bottom]), r=np.array([0.5, 8.0]),
+                      rotation=vis.pose_to_rotation_matrix_cpu(img_opk.numpy()),
+                      proj_idx=idx, dist=dist, x_proj=xp, y_proj=yp)
+        splat = vis.equirectangular_splat_cpu(xp.numpy(), yp.numpy(), dist.numpy(), img_size=(W, H),
+                                              crop_top=crop_top, crop_bottom=crop_bottom, voxel=0.05,
+                                              k_swell=1.0, d_swell=1000)
+        arrays["splat"] = splat
+        for exact in (False, True):
+            i2, xpix, ypix = vis.visibility_from_splatting_cpu(
+                xp, yp, dist, xyz[idx], img_size=(W, H), crop_top=crop_top, crop_bottom=crop_bottom,
+                voxel=0.05, k_swell=1.0, d_swell=1000, exact=exact, camera="s3dis_equirectangular")
+            arrays[f"vis_idx_{int(exact)}"] = i2
+            arrays[f"vis_x_{int(exact)}"] = xpix
+            arrays[f"vis_y_{int(exact)}"] = ypix
+        save(f"zbuffer_{tag}", **arrays)
+
+    # pinhole splat boxes (scannet-like intrinsics), numba pinhole_splat_cpu (visibility.py:761-827)
+    intr = np.eye(4, dtype=np.float32)
+    intr[0, 0], intr[1, 1], intr[0, 2], intr[1, 2] = 577.87, 577.87, 319.5, 239.5
+    m2 = 5000
+    xp = (torch.rand(m2, generator=gen).double() * 640).numpy()
+    yp = (torch.rand(m2, generator=gen).double() * 480).numpy()
+    d = (torch.rand(m2, generator=gen) * 6 + 0.3).numpy()
+    sp = vis.pinhole_splat_cpu(xp, yp, d, intr, img_size=(640, 480), crop_top=0, crop_bottom=0,
+                               voxel=0.03, k_swell=1.0, d_swell=1000)
+    save("splat_pinhole", x_proj=xp, y_proj=yp, dist=d, fx=np.array(577.87, dtype=np.float32),
+         fy=np.array(577.87, dtype=np.float32), size=np.array([640, 480]), splat=sp)
+
+
+if __name__ == "__main__":
+    main()
