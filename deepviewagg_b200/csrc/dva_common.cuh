@@ -6,15 +6,16 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <atomic>
 #include "../../include/dva_b200.h"
 
 namespace dva {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 
-// ---- thread-local error string + launch counter (C ABI: dva_last_error / dva_launch_count)
+// ---- thread-local error string + launch counter (C ABI: dva_last_error), process-wide launch counter (dva_launch_count)
 char* tls_error_buf();
-int64_t& tls_launch_count();
+std::atomic<int64_t>& launch_counter();
 
 inline int fail(int code, const char* msg) {
   snprintf(tls_error_buf(), 256, "%s", msg);
@@ -22,7 +23,7 @@ inline int fail(int code, const char* msg) {
 }
 
 inline int check_launch(const char* what) {
-  tls_launch_count() += 1;
+  launch_counter().fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(tls_error_buf(), 256, "%s: %s", what, cudaGetErrorString(e));

@@ -7,12 +7,15 @@
 //   pooling.py:293-300 / 523    out = y * expand_group_feat(Gating(segment_csr(compat,'max')))
 // which materialises >= 4 [V,C] temporaries in the reference.
 //
-// Work decomposition: one warp owns one point (CSR segment) at a time.  A feature row of C
-// channels is split into 16-byte chunks; LPR lanes cover one row (LPR*CPL chunks), so a warp
-// reads 32/LPR rows per step with every lane issuing one LDG.128 -- for C=128 fp32 a row is
-// exactly one 512 B warp-wide load.  Scores live in the flat (view,group) order of `compat`
-// so that lane l always owns group l%G; per-group max / sum are xor-shuffle reductions over
-// the lanes of equal l%G.  Everything is fp32 in registers; rows are never re-read.
+// Work decomposition: one warp owns one point (CSR segment) at a time; CTAs are persistent
+// (148 SMs x occupancy) and stride over the points.  A feature row of C channels is split into
+// 16-byte chunks; LPR lanes cover one row (LPR*CPL chunks), so a warp reads 32/LPR rows per step
+// with every lane issuing one LDG.128 -- for C=128 fp32 a row is exactly one 512 B warp-wide
+// load, kUnroll of them in flight per lane.  Scores live in the flat (view,group) order of
+// `compat` so that lane l always owns group l%G; per-group max / sum are xor-shuffle reductions
+// over the lanes of equal l%G.  Per view the inner loop is: LDS row id, IMAD.WIDE address,
+// LDG.128, LDS attention, VEC FFMAs -- the kernels are sized to stay below the ~90 warp
+// instructions per 512 B that the issue slots allow at full HBM bandwidth.
 //
 // HBM bytes per launch (s = sizeof(T)):
 //   fwd: V*(C*s + 4 + 4G) + N*(8 + C*s) (+ N*12G saved statistics when training)
@@ -37,32 +40,39 @@ struct VAParams {
 
 constexpr int kWarps = 8;          // warps per CTA
 constexpr int kUnroll = 8;         // row loads in flight per lane (x CPL)
+constexpr int kTileStride = 33;    // att tile is [G][33]: (g,v) -> bank (g+v)%32, conflict-free
 
 // A row chunk in flight: the raw 16 bytes (or one scalar) -- unpacked to fp32 only at use so
 // that kUnroll loads cost 4 registers each whatever the storage type.
 template <typename T, int VEC> struct Chunk {
   uint4 raw;
-  __device__ __forceinline__ void load(const T* p) { raw = ldg_stream16(p); }
-  __device__ __forceinline__ void zero() { raw = make_uint4(0u, 0u, 0u, 0u); }
+  __device__ __forceinline__ void load(const void* p) { raw = ldg_stream16(p); }
   __device__ __forceinline__ void get(float (&f)[VEC]) const { unpack16<T, VEC>(raw, f); }
 };
 template <typename T> struct Chunk<T, 1> {
   T raw;
-  __device__ __forceinline__ void load(const T* p) { raw = __ldg(p); }
-  __device__ __forceinline__ void zero() { raw = Cvt<T>::from_f(0.f); }
+  __device__ __forceinline__ void load(const void* p) { raw = __ldg(reinterpret_cast<const T*>(p)); }
   __device__ __forceinline__ void get(float (&f)[1]) const { f[0] = Cvt<T>::to_f(raw); }
 };
 template <typename T, int VEC>
-__device__ __forceinline__ void load_chunk(const T* p, float (&f)[VEC]) {
+__device__ __forceinline__ void load_chunk(const void* p, float (&f)[VEC]) {
   Chunk<T, VEC> c; c.load(p); c.get(f);
 }
 template <typename T, int VEC>
-__device__ __forceinline__ void store_chunk(T* p, const float (&f)[VEC]) {
+__device__ __forceinline__ void store_chunk(void* p, const float (&f)[VEC]) {
   if constexpr (VEC == 1) {
-    *p = Cvt<T>::from_f(f[0]);
+    *reinterpret_cast<T*>(p) = Cvt<T>::from_f(f[0]);
   } else {
     stg_stream16(p, pack16<T, VEC>(f));
   }
+}
+
+// byte address of row `row`: one IMAD.WIDE.U32 (row and row_bytes are 32-bit)
+__device__ __forceinline__ const char* row_addr(const char* base, uint32_t row, uint32_t row_bytes) {
+  return base + (uint64_t)row * row_bytes;
+}
+__device__ __forceinline__ char* row_addr(char* base, uint32_t row, uint32_t row_bytes) {
+  return base + (uint64_t)row * row_bytes;
 }
 
 // reduce over the lanes that share (lane % G): offsets 16 .. G
@@ -71,11 +81,59 @@ __device__ __forceinline__ float group_lane_sum(float v, int G) {
   return v;
 }
 
+// Per-point softmax statistics over the flat (view, group) scores of one segment.
+// Lane l owns elements e = l, l+32, ... (all of group l % G).  The first kCache elements per lane
+// stay in registers between the max pass and the exp pass.  `park`: segments of <= 32 views
+// leave their e-values in the [G][33] tile so the row loop needs no second exp pass.
+constexpr int kCache = 4;
+struct SegStats { float m, den; int am; };
+
+__device__ __forceinline__ SegStats seg_softmax_stats(const float* __restrict__ cp, int nG, int G,
+                                                      int lane, float inv_sq, bool park,
+                                                      float* __restrict__ tile) {
+  float c[kCache];
+  float m = -INFINITY; int am = 0x7fffffff;
+#pragma unroll
+  for (int j = 0; j < kCache; ++j) {
+    const int e = lane + 32 * j;
+    c[j] = (e < nG) ? __ldg(cp + e) : -INFINITY;
+    if (c[j] > m) { m = c[j]; am = e; }
+  }
+  for (int e = lane + 32 * kCache; e < nG; e += 32) {
+    const float v = __ldg(cp + e);
+    if (v > m) { m = v; am = e; }
+  }
+  for (int off = 16; off >= G; off >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, off);
+    const int oa = __shfl_xor_sync(0xffffffffu, am, off);
+    if (om > m || (om == m && oa < am)) { m = om; am = oa; }
+  }
+  const int gl = lane % G;
+  float den = 0.f;
+#pragma unroll
+  for (int j = 0; j < kCache; ++j) {
+    const int e = lane + 32 * j;
+    if (e < nG) {
+      const float ev = expf((c[j] - m) * inv_sq);
+      den += ev;
+      if (park) tile[gl * kTileStride + e / G] = ev;
+    }
+  }
+  for (int e = lane + 32 * kCache; e < nG; e += 32) {
+    const float ev = expf((__ldg(cp + e) - m) * inv_sq);
+    den += ev;
+    if (park) tile[gl * kTileStride + e / G] = ev;
+  }
+  den = group_lane_sum(den, G);
+  SegStats r; r.m = m; r.den = den; r.am = am;   // am: flat element index e = v*G + g
+  return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-template <typename T, int VEC, int LPR, int CPL>
-__global__ void __launch_bounds__(kWarps * 32)
+template <typename T, int VEC, int LPR, int CPL, int MINB>
+__global__ void __launch_bounds__(kWarps * 32, MINB)
 view_attention_fwd_kernel(const VAParams P) {
   constexpr int RPI = 32 / LPR;              // rows per warp step
   constexpr int TILE_C = VEC * LPR * CPL;    // channels per pass
@@ -83,133 +141,177 @@ view_attention_fwd_kernel(const VAParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = P.C, G = P.G;
-  float* att_s = reinterpret_cast<float*>(smem_raw) + warp * (32 * G);
-  int64_t* row_s = reinterpret_cast<int64_t*>(smem_raw + (size_t)kWarps * 32 * G * sizeof(float)) + warp * 32;
+  float* att_s = reinterpret_cast<float*>(smem_raw) + warp * (G * kTileStride);
+  uint32_t* row_s = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kWarps * G * kTileStride * sizeof(float)) + warp * 32;
   const int sg = lane / LPR, lir = lane % LPR;
-  const T* __restrict__ x = reinterpret_cast<const T*>(P.x);
-  T* __restrict__ out = reinterpret_cast<T*>(P.out);
+  const char* __restrict__ xb = reinterpret_cast<const char*>(P.x);
+  char* __restrict__ ob = reinterpret_cast<char*>(P.out);
+  const uint32_t row_bytes = (uint32_t)C * sizeof(T);
   const int gl = lane % G;                   // group owned by this lane in the flat score order
   const bool gating = P.gate_w != nullptr;
   const float gw = gating ? P.gate_w[gl] : 0.f, gb = gating ? P.gate_b[gl] : 0.f;
+  const bool single_tile = C <= TILE_C;
+  const bool has_idx = P.idx != nullptr;
+
+  // Per-lane chunk geometry of tile 0, hoisted out of the point loop.  Lanes past the end of
+  // the row load a clamped (valid) chunk and simply never store.
+  int gk0[CPL]; uint32_t off0[CPL]; bool live0[CPL];
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) {
+    const int c0 = (lir + LPR * k) * VEC;
+    live0[k] = c0 < C;
+    const int cc = live0[k] ? c0 : 0;
+    gk0[k] = group_of_channel(cc, C, G);      // VEC>1: host guarantees chunks never straddle groups
+    off0[k] = (uint32_t)cc * sizeof(T);
+  }
 
   const int64_t warps_total = (int64_t)gridDim.x * kWarps;
   for (int64_t i = (int64_t)blockIdx.x * kWarps + warp; i < P.N; i += warps_total) {
     const int64_t p0 = P.ptr[i];
     const int n = (int)(P.ptr[i + 1] - p0);
+    __syncwarp();                            // att_s / row_s of the previous point are free
+    if (n == 0) {                            // unseen point: exact zeros (segment_csr of nothing)
+      if (lane < G && P.seg_max != nullptr) {
+        P.seg_max[i * G + lane] = 0.f; P.seg_den[i * G + lane] = P.eps; P.seg_arg[i * G + lane] = -1;
+      }
+      if (sg == 0) {
+        float z[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) z[j] = 0.f;
+        for (int c0 = lir * VEC; c0 < C; c0 += LPR * VEC)
+          store_chunk<T, VEC>(ob + i * (int64_t)row_bytes + (size_t)c0 * sizeof(T), z);
+      }
+      continue;
+    }
     const int nG = n * G;
     const float* __restrict__ cp = P.compat + p0 * G;
-
-    // ---- per-group max (first arg-max) and softmax denominator
-    float m = -INFINITY; int am = 0x7fffffff;
-    for (int e = lane; e < nG; e += 32) {
-      const float c = __ldg(cp + e);
-      if (c > m) { m = c; am = e / G; }
-    }
-    for (int off = 16; off >= G; off >>= 1) {
-      const float om = __shfl_xor_sync(0xffffffffu, m, off);
-      const int oa = __shfl_xor_sync(0xffffffffu, am, off);
-      if (om > m || (om == m && oa < am)) { m = om; am = oa; }
-    }
-    if (n == 0) { m = 0.f; am = -1; }        // segment_csr(max) of an empty segment is 0
-    const float sq = (P.group_scaling && n > 0) ? sqrtf((float)n) : 1.f;
-    float den = 0.f;
-    for (int e = lane; e < nG; e += 32) den += expf((__ldg(cp + e) - m) / sq);
-    den = group_lane_sum(den, G) + P.eps;
-    const float t = gating ? tanhf(fmaxf(fmaf(gw, m, gb), 0.f)) : 1.f;
+    // reference: (c - max) / sqrt(n) (pooling.py:792-801); one reciprocal per point instead
+    const float inv_sq = P.group_scaling ? rsqrtf((float)n) : 1.f;
+    const bool one_chunk = n <= 32;
+    const SegStats st = seg_softmax_stats(cp, nG, G, lane, inv_sq, one_chunk, att_s);
+    const float den = st.den + P.eps;
+    const float t = gating ? tanhf(fmaxf(fmaf(gw, st.m, gb), 0.f)) : 1.f;
     if (lane < G && P.seg_max != nullptr) {
-      P.seg_max[i * G + lane] = m;
+      P.seg_max[i * G + lane] = st.m;
       P.seg_den[i * G + lane] = den;
-      P.seg_arg[i * G + lane] = (n > 0) ? (int32_t)(p0 + am) : -1;
+      P.seg_arg[i * G + lane] = (int32_t)(p0 + st.am / G);
     }
+    const float inv_den = 1.f / den;
+    const float scale = t * inv_den;         // applied once per output channel instead of per view
 
     for (int ct = 0; ct < C; ct += TILE_C) {
       float acc[CPL][VEC];
-      int gk[CPL][VEC];
+      int gk[CPL]; uint32_t off[CPL]; bool live[CPL];
 #pragma unroll
-      for (int k = 0; k < CPL; ++k)
+      for (int k = 0; k < CPL; ++k) {
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-          acc[k][j] = 0.f;
-          const int c = ct + (lir + LPR * k) * VEC + j;
-          gk[k][j] = group_of_channel(c < C ? c : C - 1, C, G);
+        for (int j = 0; j < VEC; ++j) acc[k][j] = 0.f;
+        if (single_tile) {
+          gk[k] = gk0[k]; off[k] = off0[k]; live[k] = live0[k];
+        } else {
+          const int c0 = ct + (lir + LPR * k) * VEC;
+          live[k] = c0 < C;
+          const int cc = live[k] ? c0 : 0;
+          gk[k] = group_of_channel(cc, C, G);
+          off[k] = (uint32_t)cc * sizeof(T);
         }
+      }
 
       for (int vs = 0; vs < n; vs += 32) {
         const int nc = min(32, n - vs);
-        __syncwarp();
-        for (int e = lane; e < nc * G; e += 32) {
-          const float a = expf((__ldg(cp + vs * G + e) - m) / sq) / den;
-          att_s[e] = a;
-          if (ct == 0 && P.att != nullptr) P.att[(p0 + vs) * G + e] = a;
+        if (!one_chunk) {                    // long segments: e-values of this chunk
+          __syncwarp();
+          for (int e = lane; e < nc * G; e += 32)
+            att_s[gl * kTileStride + e / G] = expf((__ldg(cp + vs * G + e) - st.m) * inv_sq);
         }
-        if (lane < nc) row_s[lane] = load_idx(P.idx, P.idx64, p0 + vs + lane);
+        if (lane < nc)
+          row_s[lane] = has_idx ? (uint32_t)load_idx(P.idx, P.idx64, p0 + vs + lane)
+                                : (uint32_t)(p0 + vs + lane);
         __syncwarp();
 
-        for (int v0 = 0; v0 < nc; v0 += RPI * U) {
+        const uint32_t* rs = row_s + sg;     // this sub-group's row of each step
+        const float* as[CPL];
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) as[k] = att_s + gk[k] * kTileStride + sg;
+        int v0 = 0;
+        // ---- main loop: U full row steps, no predicates
+        for (; v0 + RPI * U <= nc; v0 += RPI * U) {
           Chunk<T, VEC> f[U][CPL];
-          bool ok[U];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const int v = v0 + u * RPI + sg;
-            ok[u] = v < nc;
-            const T* rp = x + row_s[ok[u] ? v : 0] * (int64_t)C + ct;
+            const char* rp = row_addr(xb, rs[v0 + u * RPI], row_bytes);
 #pragma unroll
-            for (int k = 0; k < CPL; ++k) {
-              const int c0 = (lir + LPR * k) * VEC;
-              if (ok[u] && ct + c0 < C) f[u][k].load(rp + c0); else f[u][k].zero();
-            }
+            for (int k = 0; k < CPL; ++k) f[u][k].load(rp + off[k]);
           }
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const int v = ok[u] ? v0 + u * RPI + sg : 0;
 #pragma unroll
             for (int k = 0; k < CPL; ++k) {
               float fv[VEC];
               f[u][k].get(fv);
-              // a chunk usually lies inside one group: one LDS broadcast per chunk
-              const float a0 = att_s[v * G + gk[k][0]];
+              const float a = as[k][v0 + u * RPI];
 #pragma unroll
-              for (int j = 0; j < VEC; ++j) {
-                const float a = (j == 0 || gk[k][j] == gk[k][0]) ? a0 : att_s[v * G + gk[k][j]];
-                acc[k][j] = fmaf(a, fv[j], acc[k][j]);
-              }
+              for (int j = 0; j < VEC; ++j) acc[k][j] = fmaf(a, fv[j], acc[k][j]);
+            }
+          }
+        }
+        // ---- tail: one row step at a time
+        for (; v0 < nc; v0 += RPI) {
+          if (v0 + sg < nc) {
+            const char* rp = row_addr(xb, rs[v0], row_bytes);
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+              float fv[VEC];
+              load_chunk<T, VEC>(rp + off[k], fv);
+              const float a = as[k][v0];
+#pragma unroll
+              for (int j = 0; j < VEC; ++j) acc[k][j] = fmaf(a, fv[j], acc[k][j]);
             }
           }
         }
       }
 
-      // combine the RPI row sub-groups, apply gating, store
+      // combine the RPI row sub-groups, apply gating and 1/den, store
 #pragma unroll
-      for (int k = 0; k < CPL; ++k)
+      for (int k = 0; k < CPL; ++k) {
+        const float sc = __shfl_sync(0xffffffffu, scale, gk[k]);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
           float a = acc[k][j];
 #pragma unroll
-          for (int off = LPR; off < 32; off <<= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-          acc[k][j] = a * __shfl_sync(0xffffffffu, t, gk[k][j]);
+          for (int o = LPR; o < 32; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+          acc[k][j] = a * sc;
         }
+      }
       if (sg == 0) {
 #pragma unroll
-        for (int k = 0; k < CPL; ++k) {
-          const int c0 = ct + (lir + LPR * k) * VEC;
-          if (c0 < C) store_chunk<T, VEC>(out + i * (int64_t)C + c0, acc[k]);
-        }
+        for (int k = 0; k < CPL; ++k)
+          if (live[k]) store_chunk<T, VEC>(ob + i * (int64_t)row_bytes + off[k], acc[k]);
+      }
+    }
+
+    if (P.att != nullptr) {                  // save_last tap / autograd: normalised attentions
+      float* __restrict__ ao = P.att + p0 * G;
+      if (one_chunk) {
+        for (int e = lane; e < nG; e += 32) ao[e] = att_s[gl * kTileStride + e / G] * inv_den;
+      } else {
+        for (int e = lane; e < nG; e += 32) ao[e] = expf((__ldg(cp + e) - st.m) * inv_sq) * inv_den;
       }
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward
-//   s_vg   = sum_{c in g} dO_c x_vc            (one dot product per view and group)
-//   S_g    = sum_v a_vg s_vg   (= d/dt_g)
-//   dx_vc  = a_vg t_g dO_c
-//   dc_vg  = a_vg t_g (s_vg - S_g)/sqrt(n)  +  [v == argmax_g] S_g (1-t_g^2) w_g 1[w q + b > 0]
-//   dw_g  += S_g (1-t^2) 1[.] q_g ;  db_g += S_g (1-t^2) 1[.]
+// backward.  With gd = dO * t (gate folded into the upstream gradient):
+//   s'_vg  = sum_{c in g} gd_c x_vc           (one dot product per view and group)
+//   S'_g   = sum_v a_vg s'_vg                 (= t_g * dL/dt_g)
+//   dx_vc  = a_vg gd_c
+//   dc_vg  = a_vg (s'_vg - S'_g)/sqrt(n)  +  [v == argmax_g] (S'_g/t_g) (1-t_g^2) w_g 1[w q + b > 0]
+//   dw_g  += (S'_g/t_g) (1-t^2) 1[.] q_g ;  db_g += (S'_g/t_g) (1-t^2) 1[.]
 // (the reference obtains the same through autograd over pooling.py:285-300.)
 // ---------------------------------------------------------------------------------------------
-template <typename T, int VEC, int LPR, int CPL>
-__global__ void __launch_bounds__(kWarps * 32)
+template <typename T, int VEC, int LPR, int CPL, int MINB>
+__global__ void __launch_bounds__(kWarps * 32, MINB)
 view_attention_bwd_kernel(const VAParams P) {
   constexpr int RPI = 32 / LPR;
   constexpr int TILE_C = VEC * LPR * CPL;
@@ -217,24 +319,40 @@ view_attention_bwd_kernel(const VAParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = P.C, G = P.G;
-  float* att_s = reinterpret_cast<float*>(smem_raw) + warp * (32 * G);
-  float* s_s = reinterpret_cast<float*>(smem_raw) + (kWarps + warp) * (32 * G);
-  int64_t* row_s = reinterpret_cast<int64_t*>(smem_raw + (size_t)2 * kWarps * 32 * G * sizeof(float)) + warp * 32;
-  float* gate_s = reinterpret_cast<float*>(smem_raw + (size_t)2 * kWarps * 32 * G * sizeof(float) +
-                                           (size_t)kWarps * 32 * sizeof(int64_t));  // [kWarps][2][G]
+  const int tile = G * kTileStride;
+  float* att_s = reinterpret_cast<float*>(smem_raw) + warp * tile;
+  float* s_s = reinterpret_cast<float*>(smem_raw) + (kWarps + warp) * tile;
+  uint32_t* row_s = reinterpret_cast<uint32_t*>(smem_raw + (size_t)2 * kWarps * tile * sizeof(float)) + warp * 32;
+  float* gate_s = reinterpret_cast<float*>(smem_raw + (size_t)2 * kWarps * tile * sizeof(float) +
+                                           (size_t)kWarps * 32 * sizeof(uint32_t));  // [kWarps][2][G]
   const int sg = lane / LPR, lir = lane % LPR;
-  const T* __restrict__ x = reinterpret_cast<const T*>(P.x);
-  const T* __restrict__ gout = reinterpret_cast<const T*>(P.gout);
-  T* __restrict__ gx = reinterpret_cast<T*>(P.gx);
+  const char* __restrict__ xb = reinterpret_cast<const char*>(P.x);
+  const char* __restrict__ gob = reinterpret_cast<const char*>(P.gout);
+  char* __restrict__ gxb = reinterpret_cast<char*>(P.gx);
+  const uint32_t row_bytes = (uint32_t)C * sizeof(T);
   const int gl = lane % G;
   const bool gating = P.gate_w != nullptr;
   const float gw = gating ? P.gate_w[gl] : 0.f, gb = gating ? P.gate_b[gl] : 0.f;
   float dw_acc = 0.f, db_acc = 0.f;
+  const bool single_tile = C <= TILE_C;
+  const bool has_idx = P.idx != nullptr;
+  const bool scatter = P.scatter && has_idx;
   // How the per-(view,group) dot products are reduced across the lanes of a row:
   //   cpg = 16-byte chunks per group when all groups are equally wide and chunk-aligned.
   const int cpg = (C % G == 0 && (C / G) % VEC == 0) ? (C / G) / VEC : 0;
   const bool cpg_pow2 = cpg > 0 && (cpg & (cpg - 1)) == 0;
   const int red_mode = (cpg_pow2 && cpg <= LPR) ? 1 : ((cpg_pow2 && cpg % LPR == 0) ? 2 : 0);
+  const bool assign_s = single_tile && red_mode == 1;   // every (v,g) slot written exactly once
+
+  int gk0[CPL]; uint32_t off0[CPL]; bool live0[CPL];
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) {
+    const int c0 = (lir + LPR * k) * VEC;
+    live0[k] = c0 < C;
+    const int cc = live0[k] ? c0 : 0;
+    gk0[k] = group_of_channel(cc, C, G);
+    off0[k] = (uint32_t)cc * sizeof(T);
+  }
 
   const int64_t warps_total = (int64_t)gridDim.x * kWarps;
   for (int64_t i = (int64_t)blockIdx.x * kWarps + warp; i < P.N; i += warps_total) {
@@ -244,119 +362,152 @@ view_attention_bwd_kernel(const VAParams P) {
     const int nG = n * G;
     const float* __restrict__ cp = P.compat + p0 * G;
     float* __restrict__ gc = P.gcompat + p0 * G;
-    const float m = P.s_max[i * G + gl], den = P.s_den[i * G + gl];
+    const float m = P.s_max[i * G + gl];
+    const float inv_den = 1.f / P.s_den[i * G + gl];
     const int arg_v = P.s_arg[i * G + gl];
-    const float sq = P.group_scaling ? sqrtf((float)n) : 1.f;
+    const float inv_sq = P.group_scaling ? rsqrtf((float)n) : 1.f;
     const float z = fmaf(gw, m, gb);
     const float t = gating ? tanhf(fmaxf(z, 0.f)) : 1.f;
-    float S = 0.f;                            // sum_v a_vg s_vg for g = lane%G (partial per lane)
+    const bool one_chunk = n <= 32;
+    float S = 0.f;                            // sum_v a_vg s'_vg for g = lane%G (partial per lane)
+
+    // gd = dO * t of this lane's channels (single channel tile: loaded once per point)
+    float gd[CPL][VEC];
+    int gk[CPL]; uint32_t off[CPL]; bool live[CPL];
+    auto load_gd = [&](int ct) {
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        if (single_tile) {
+          gk[k] = gk0[k]; off[k] = off0[k]; live[k] = live0[k];
+        } else {
+          const int c0 = ct + (lir + LPR * k) * VEC;
+          live[k] = c0 < C;
+          const int cc = live[k] ? c0 : 0;
+          gk[k] = group_of_channel(cc, C, G);
+          off[k] = (uint32_t)cc * sizeof(T);
+        }
+        const float tk = __shfl_sync(0xffffffffu, t, gk[k]);
+        load_chunk<T, VEC>(gob + i * (int64_t)row_bytes + off[k], gd[k]);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) gd[k][j] = live[k] ? gd[k][j] * tk : 0.f;   // dead lanes add 0
+      }
+    };
+    if (single_tile) load_gd(0);
 
     for (int vs = 0; vs < n; vs += 32) {
       const int nc = min(32, n - vs);
       __syncwarp();
       for (int e = lane; e < nc * G; e += 32) {
-        att_s[e] = expf((__ldg(cp + vs * G + e) - m) / sq) / den;
-        s_s[e] = 0.f;
+        const int slot = gl * kTileStride + e / G;
+        att_s[slot] = expf((__ldg(cp + vs * G + e) - m) * inv_sq) * inv_den;
+        if (!assign_s) s_s[slot] = 0.f;
       }
-      if (lane < nc) row_s[lane] = load_idx(P.idx, P.idx64, p0 + vs + lane);
+      if (lane < nc)
+        row_s[lane] = has_idx ? (uint32_t)load_idx(P.idx, P.idx64, p0 + vs + lane)
+                              : (uint32_t)(p0 + vs + lane);
       __syncwarp();
+      const uint32_t out_row0 = (uint32_t)(p0 + vs);
 
       for (int ct = 0; ct < C; ct += TILE_C) {
-        float go[CPL][VEC];                   // dO of this lane's channels
-        int gk[CPL];                          // group of each chunk (chunks never straddle groups)
-        float tk[CPL];                        // gate value of that group
+        if (!single_tile) load_gd(ct);
+        const uint32_t* rs = row_s + sg;
+        const float* as[CPL]; float* ss[CPL];
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
-          const int c0 = ct + (lir + LPR * k) * VEC;
-          gk[k] = group_of_channel(c0 < C ? c0 : C - 1, C, G);
-          tk[k] = __shfl_sync(0xffffffffu, t, gk[k]);
-          if (c0 < C) {
-            load_chunk<T, VEC>(gout + i * (int64_t)C + c0, go[k]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) go[k][j] = 0.f;
-          }
+          as[k] = att_s + gk[k] * kTileStride + sg;
+          ss[k] = s_s + gk[k] * kTileStride + sg;
         }
 
-        for (int v0 = 0; v0 < nc; v0 += RPI * U) {
+        // one row step: x chunk(s) of view v0+sg -> dx store + per-group dot product into s_s
+        auto consume = [&](int v0, const Chunk<T, VEC> (&f)[CPL], uint32_t srow, bool ok) {
+          const uint32_t orow = scatter ? srow : out_row0 + (uint32_t)(v0 + sg);
+          char* op = row_addr(gxb, orow, row_bytes);
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) {
+            float fv[VEC], dx[VEC];
+            f[k].get(fv);
+            const float a = as[k][v0];
+            float dot = 0.f;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+              dot = fmaf(gd[k][j], fv[j], dot);
+              dx[j] = a * gd[k][j];
+            }
+            const bool lv = ok && live[k];
+            if (lv) store_chunk<T, VEC>(op + off[k], dx);
+            if (red_mode == 1) {              // groups = aligned blocks of cpg lanes
+              float r = dot;
+              for (int o = 1; o < cpg; o <<= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+              if (lv && (lir & (cpg - 1)) == 0) {
+                if (assign_s) ss[k][v0] = r; else ss[k][v0] += r;
+              }
+            } else if (red_mode == 2) {       // the whole row step lies in one group
+              float r = dot;
+#pragma unroll
+              for (int o = 1; o < LPR; o <<= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+              if (lv && lir == 0) ss[k][v0] += r;
+            } else {                          // irregular group sizes: one reduction per group
+              for (int g = 0; g < G; ++g) {
+                const bool mine = lv && (gk[k] == g);
+                if (!__any_sync(0xffffffffu, mine)) continue;
+                float r = mine ? dot : 0.f;
+#pragma unroll
+                for (int o = 1; o < LPR; o <<= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+                if (ok && lir == 0) s_s[g * kTileStride + sg + v0] += r;
+              }
+            }
+          }
+        };
+
+        int v0 = 0;
+        for (; v0 + RPI * U <= nc; v0 += RPI * U) {
           Chunk<T, VEC> f[U][CPL];
-          bool ok[U];
+          uint32_t srow[U];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const int v = v0 + u * RPI + sg;
-            ok[u] = v < nc;
-            const T* rp = x + row_s[ok[u] ? v : 0] * (int64_t)C + ct;
+            srow[u] = rs[v0 + u * RPI];
+            const char* rp = row_addr(xb, srow[u], row_bytes);
 #pragma unroll
-            for (int k = 0; k < CPL; ++k) {
-              const int c0 = (lir + LPR * k) * VEC;
-              if (ok[u] && ct + c0 < C) f[u][k].load(rp + c0); else f[u][k].zero();
-            }
+            for (int k = 0; k < CPL; ++k) f[u][k].load(rp + off[k]);
           }
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int vv = ok[u] ? v0 + u * RPI + sg : 0;
-            const int64_t orow = (P.scatter && P.idx != nullptr) ? row_s[vv] : (p0 + vs + vv);
+          for (int u = 0; u < U; ++u) consume(v0 + u * RPI, f[u], srow[u], true);
+        }
+        for (; v0 < nc; v0 += RPI) {           // tail; idle sub-groups still join the shuffles
+          const bool ok = v0 + sg < nc;
+          Chunk<T, VEC> f[CPL];
+          const uint32_t srow = ok ? rs[v0] : row_s[0];   // idle lanes re-read a valid row
+          const char* rp = row_addr(xb, srow, row_bytes);
 #pragma unroll
-            for (int k = 0; k < CPL; ++k) {
-              const int c0 = ct + (lir + LPR * k) * VEC;
-              const bool live = ok[u] && c0 < C;
-              float fv[VEC], dx[VEC];
-              f[u][k].get(fv);
-              float dot = 0.f;
-              const float a_t = att_s[vv * G + gk[k]] * tk[k];
-#pragma unroll
-              for (int j = 0; j < VEC; ++j) {
-                dot = fmaf(go[k][j], fv[j], dot);
-                dx[j] = a_t * go[k][j];
-              }
-              if (live) store_chunk<T, VEC>(gx + orow * (int64_t)C + c0, dx);
-              // ---- s_vg += sum over the lanes of this row whose chunk lies in group g
-              if (red_mode == 1) {            // groups = aligned blocks of cpg lanes
-                float r = dot;
-                for (int off = 1; off < cpg; off <<= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
-                if (live && (lir & (cpg - 1)) == 0) s_s[vv * G + gk[k]] += r;
-              } else if (red_mode == 2) {     // the whole row step lies in one group
-                float r = dot;
-#pragma unroll
-                for (int off = 1; off < LPR; off <<= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
-                if (live && lir == 0) s_s[vv * G + gk[k]] += r;
-              } else {                        // irregular group sizes: one reduction per group
-                for (int g = 0; g < G; ++g) {
-                  const bool mine = live && (gk[k] == g);
-                  if (!__any_sync(0xffffffffu, mine)) continue;
-                  float r = mine ? dot : 0.f;
-#pragma unroll
-                  for (int off = 1; off < LPR; off <<= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
-                  if (ok[u] && lir == 0) s_s[vv * G + g] += r;
-                }
-              }
-            }
-          }
+          for (int k = 0; k < CPL; ++k) f[k].load(rp + off[k]);
+          consume(v0, f, srow, ok);
         }
         __syncwarp();
       }
 
-      // S partial and raw s -> grad_compat (finalised below once S is complete)
-      __syncwarp();
+      // S partial; raw s' -> grad_compat for long segments (finalised below once S is complete)
       for (int e = lane; e < nc * G; e += 32) {
-        const float s = s_s[e];
-        S = fmaf(att_s[e], s, S);
-        gc[vs * G + e] = s;
+        const int slot = gl * kTileStride + e / G;
+        const float sv = s_s[slot];
+        S = fmaf(att_s[slot], sv, S);
+        if (!one_chunk) gc[vs * G + e] = sv;
       }
     }
 
     S = group_lane_sum(S, G);
     const float one_m_t2 = 1.f - t * t;
-    const float dq = (gating && z > 0.f) ? S * one_m_t2 * gw : 0.f;
-    if (gating && z > 0.f && lane < G) {
-      dw_acc += S * one_m_t2 * m;
-      db_acc += S * one_m_t2;
+    const float dLdt = (t != 0.f) ? S / t : 0.f;
+    const bool open = gating && z > 0.f;
+    const float dq = open ? dLdt * one_m_t2 * gw : 0.f;
+    if (open && lane < G) {
+      dw_acc += dLdt * one_m_t2 * m;
+      db_acc += dLdt * one_m_t2;
     }
-    __syncwarp();
     for (int e = lane; e < nG; e += 32) {
-      const float a = expf((__ldg(cp + e) - m) / sq) / den;
-      const float s = gc[e];
-      float d = a * t * (s - S) / sq;
+      float a, sv;
+      if (one_chunk) { const int slot = gl * kTileStride + e / G; a = att_s[slot]; sv = s_s[slot]; }
+      else { a = expf((__ldg(cp + e) - m) * inv_sq) * inv_den; sv = gc[e]; }
+      float d = a * (sv - S) * inv_sq;
       if (p0 + e / G == arg_v) d += dq;
       gc[e] = d;
     }
@@ -413,29 +564,46 @@ static VAConfig choose_config(const VAParams& P, const void* o1, const void* o2)
   return cfg;
 }
 
-static int va_grid(int64_t N) {
-  int64_t blocks = (N + kWarps - 1) / kWarps;
-  const int64_t cap = (int64_t)kNumSMs * 8;
-  if (blocks > cap) blocks = cap;
+// persistent grid: exactly the number of CTAs that are co-resident (148 SMs x occupancy), so the
+// grid-stride point loop has no second wave; never more CTAs than there are point groups.
+template <typename K>
+static int va_grid(K kern, size_t smem, int64_t N) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarps * 32, smem) != cudaSuccess || occ < 1) occ = 2;
+  int64_t blocks = (int64_t)kNumSMs * occ;
+  const int64_t need = (N + kWarps - 1) / kWarps;
+  if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
 }
 
+constexpr int kMinBlocksFwd = 4;   // 32 warps / SM
+constexpr int kMinBlocksBwd = 3;   // 24 warps / SM
+
+static size_t fwd_smem(int G) {
+  return (size_t)kWarps * G * kTileStride * sizeof(float) + (size_t)kWarps * 32 * sizeof(uint32_t);
+}
+static size_t bwd_smem(int G) {
+  return (size_t)2 * kWarps * G * kTileStride * sizeof(float) + (size_t)kWarps * 32 * sizeof(uint32_t) +
+         (size_t)kWarps * 2 * G * sizeof(float);
+}
+
 template <typename T, int VEC, int LPR, int CPL>
 static int launch_fwd(const VAParams& P, cudaStream_t st) {
-  const size_t smem = (size_t)kWarps * 32 * P.G * sizeof(float) + (size_t)kWarps * 32 * sizeof(int64_t);
-  auto kern = view_attention_fwd_kernel<T, VEC, LPR, CPL>;
+  const size_t smem = fwd_smem(P.G);
+  auto kern = view_attention_fwd_kernel<T, VEC, LPR, CPL, (CPL >= 4 ? 2 : kMinBlocksFwd)>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  kern<<<va_grid(P.N), kWarps * 32, smem, st>>>(P);
+  kern<<<va_grid(kern, smem, P.N), kWarps * 32, smem, st>>>(P);
   return check_launch("view_attention_fwd");
 }
 
 template <typename T, int VEC, int LPR, int CPL>
-static int launch_bwd(const VAParams& P, int grid, cudaStream_t st) {
-  const size_t smem = (size_t)2 * kWarps * 32 * P.G * sizeof(float) + (size_t)kWarps * 32 * sizeof(int64_t) +
-                      (size_t)kWarps * 2 * P.G * sizeof(float);
-  auto kern = view_attention_bwd_kernel<T, VEC, LPR, CPL>;
+static int launch_bwd(const VAParams& P, int* grid_out, cudaStream_t st) {
+  const size_t smem = bwd_smem(P.G);
+  auto kern = view_attention_bwd_kernel<T, VEC, LPR, CPL, (CPL >= 4 ? 2 : kMinBlocksBwd)>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int grid = va_grid(kern, smem, P.N);
+  *grid_out = grid;
   kern<<<grid, kWarps * 32, smem, st>>>(P);
   return check_launch("view_attention_bwd");
 }
@@ -459,7 +627,7 @@ template <typename T> static int fwd_typed(const VAParams& P, cudaStream_t st) {
   const VAConfig cfg = choose_config<T>(P, P.out, nullptr);
   DVA_VA_DISPATCH(launch_fwd, T, cfg, P, st);
 }
-template <typename T> static int bwd_typed(const VAParams& P, int grid, cudaStream_t st) {
+template <typename T> static int bwd_typed(const VAParams& P, int* grid, cudaStream_t st) {
   const VAConfig cfg = choose_config<T>(P, P.gout, P.gx);
   DVA_VA_DISPATCH(launch_bwd, T, cfg, P, grid, st);
 }
@@ -481,6 +649,7 @@ extern "C" int dva_view_attention_fwd(const void* x, const void* idx, int idx_is
   if (G > C) return fail(DVA_EINVAL, "view_attention_fwd: num_groups > channels");
   if (!pow2_le32(G)) return fail(DVA_EUNSUPPORTED, "view_attention_fwd: G must be a power of two <= 32");
   if (C > (1 << 20)) return fail(DVA_EUNSUPPORTED, "view_attention_fwd: C too large");
+  if (R >= (1ll << 32) || V >= (1ll << 32)) return fail(DVA_EUNSUPPORTED, "view_attention_fwd: more than 2^32 rows");
   if (N == 0) return DVA_OK;
   if (!ptr || !out || (V > 0 && (!x || !compat))) return fail(DVA_EINVAL, "view_attention_fwd: null pointer");
   if ((gate_w == nullptr) != (gate_b == nullptr)) return fail(DVA_EINVAL, "view_attention_fwd: gate_w/gate_b must both be given");
@@ -501,6 +670,7 @@ extern "C" int dva_view_attention_fwd(const void* x, const void* idx, int idx_is
 }
 
 extern "C" size_t dva_view_attention_bwd_workspace_bytes(int64_t G) {
+  // one [2,G] partial per CTA of the persistent grid (at most 148 SMs x 8 co-resident CTAs)
   return (size_t)kNumSMs * 8 * 2 * (size_t)(G > 0 ? G : 1) * sizeof(float);
 }
 
@@ -516,6 +686,7 @@ extern "C" int dva_view_attention_bwd(const void* x, const void* idx, int idx_is
   if (N < 0 || V < 0 || R < 0 || C < 1 || G < 1) return fail(DVA_EINVAL, "view_attention_bwd: bad sizes");
   if (G > C) return fail(DVA_EINVAL, "view_attention_bwd: num_groups > channels");
   if (!pow2_le32(G)) return fail(DVA_EUNSUPPORTED, "view_attention_bwd: G must be a power of two <= 32");
+  if (R >= (1ll << 32) || V >= (1ll << 32)) return fail(DVA_EUNSUPPORTED, "view_attention_bwd: more than 2^32 rows");
   const bool gating = gate_w != nullptr;
   if (gating != (gate_b != nullptr)) return fail(DVA_EINVAL, "view_attention_bwd: gate_w/gate_b must both be given");
   cudaStream_t st = (cudaStream_t)stream;
@@ -534,12 +705,12 @@ extern "C" int dva_view_attention_bwd(const void* x, const void* idx, int idx_is
   P.gx = grad_x_rows; P.gcompat = grad_compat; P.scatter = scatter_rows;
   P.gate_partial = gating ? reinterpret_cast<float*>(workspace) : nullptr;
   P.N = N; P.V = V; P.R = R; P.C = (int)C; P.G = (int)G; P.group_scaling = group_scaling;
-  const int grid = va_grid(N);
+  int grid = 1;
   int rc;
   switch (dtype) {
-    case DVA_F32: rc = bwd_typed<float>(P, grid, st); break;
-    case DVA_BF16: rc = bwd_typed<__nv_bfloat16>(P, grid, st); break;
-    case DVA_F16: rc = bwd_typed<__half>(P, grid, st); break;
+    case DVA_F32: rc = bwd_typed<float>(P, &grid, st); break;
+    case DVA_BF16: rc = bwd_typed<__nv_bfloat16>(P, &grid, st); break;
+    case DVA_F16: rc = bwd_typed<__half>(P, &grid, st); break;
     default: return fail(DVA_EINVAL, "view_attention_bwd: unknown dtype");
   }
   if (rc) return rc;

@@ -39,8 +39,8 @@ enum { DVA_SUM = 0, DVA_MEAN = 1, DVA_MAX = 2, DVA_MIN = 3 };
 
 int dva_abi_version(void);
 const char* dva_last_error(void);
-/* number of kernels this library has launched from the calling thread since load
- * (bench.py reports it as gpu_launches). */
+/* number of kernels this library has launched in this process since load (all threads:
+ * autograd runs backward from a worker thread); bench.py reports it as gpu_launches. */
 int64_t dva_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------

@@ -50,8 +50,10 @@ class _SegReduce(torch.autograd.Function):
     @staticmethod
     def forward(ctx, src, dense, n_seg, reduce):
         shape = src.shape
-        src2 = src.reshape(shape[0], -1)
-        K = src2.shape[1]
+        K = 1
+        for d in shape[1:]:
+            K *= int(d)
+        src2 = src.reshape(shape[0], K)
         ctx.reduce, ctx.shape, ctx.n_seg = reduce, shape, n_seg
         counts = torch.bincount(dense, minlength=n_seg)
         if reduce in ("sum", "mean"):
@@ -76,9 +78,11 @@ class _SegReduce(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out, _grad_arg):
         shape = ctx.shape
-        g2 = grad_out.reshape(ctx.n_seg, -1)
         n_items = shape[0]
-        K = g2.shape[1]
+        K = 1
+        for d in shape[1:]:
+            K *= int(d)
+        g2 = grad_out.reshape(ctx.n_seg, K)
         if ctx.reduce in ("sum", "mean"):
             dense, counts = ctx.saved_tensors
             if ctx.reduce == "mean":
@@ -111,8 +115,10 @@ def _scatter_sorted_or_not(src, index, dim_size, reduce):
     if dim_size is None:
         dim_size = int(index.max().item()) + 1 if index.numel() > 0 else 0
     shape = src.shape
-    src2 = src.reshape(shape[0], -1)
-    K = src2.shape[1]
+    K = 1
+    for d in shape[1:]:
+        K *= int(d)
+    src2 = src.reshape(shape[0], K)
     if reduce in ("sum", "mean"):
         out = torch.zeros((dim_size, K), dtype=src.dtype, device=src.device)
         out = out.index_add(0, index, src2)
