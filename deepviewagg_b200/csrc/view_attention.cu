@@ -231,17 +231,18 @@ view_attention_fwd_kernel(const VAParams P) {
 
         const uint32_t* rs = row_s + sg;     // this sub-group's row of each step
         const float* as[CPL];
+        const char* xk[CPL];                 // per-lane base pointers: row address = 1 IMAD.WIDE
 #pragma unroll
-        for (int k = 0; k < CPL; ++k) as[k] = att_s + gk[k] * kTileStride + sg;
+        for (int k = 0; k < CPL; ++k) { as[k] = att_s + gk[k] * kTileStride + sg; xk[k] = xb + off[k]; }
         int v0 = 0;
         // ---- main loop: U full row steps, no predicates
         for (; v0 + RPI * U <= nc; v0 += RPI * U) {
           Chunk<T, VEC> f[U][CPL];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const char* rp = row_addr(xb, rs[v0 + u * RPI], row_bytes);
+            const uint32_t srow = rs[v0 + u * RPI];
 #pragma unroll
-            for (int k = 0; k < CPL; ++k) f[u][k].load(rp + off[k]);
+            for (int k = 0; k < CPL; ++k) f[u][k].load(row_addr(xk[k], srow, row_bytes));
           }
 #pragma unroll
           for (int u = 0; u < U; ++u) {
@@ -258,11 +259,11 @@ view_attention_fwd_kernel(const VAParams P) {
         // ---- tail: one row step at a time
         for (; v0 < nc; v0 += RPI) {
           if (v0 + sg < nc) {
-            const char* rp = row_addr(xb, rs[v0], row_bytes);
+            const uint32_t srow = rs[v0];
 #pragma unroll
             for (int k = 0; k < CPL; ++k) {
               float fv[VEC];
-              load_chunk<T, VEC>(rp + off[k], fv);
+              load_chunk<T, VEC>(row_addr(xk[k], srow, row_bytes), fv);
               const float a = as[k][v0];
 #pragma unroll
               for (int j = 0; j < VEC; ++j) acc[k][j] = fmaf(a, fv[j], acc[k][j]);
@@ -310,7 +311,10 @@ view_attention_fwd_kernel(const VAParams P) {
 //   dw_g  += (S'_g/t_g) (1-t^2) 1[.] q_g ;  db_g += (S'_g/t_g) (1-t^2) 1[.]
 // (the reference obtains the same through autograd over pooling.py:285-300.)
 // ---------------------------------------------------------------------------------------------
-template <typename T, int VEC, int LPR, int CPL, int MINB>
+// REG: all groups equally wide, a power-of-two number of chunks each (cpg), so the lanes of a group
+// form aligned blocks -> log2(min(cpg,LPR)) shuffle steps.  !REG: arbitrary group_sizes(C,G)
+// (pooling.py:737-745), one masked full-row reduction per group (scalar kernels only).
+template <typename T, int VEC, int LPR, int CPL, int MINB, bool REG>
 __global__ void __launch_bounds__(kWarps * 32, MINB)
 view_attention_bwd_kernel(const VAParams P) {
   constexpr int RPI = 32 / LPR;
@@ -322,9 +326,10 @@ view_attention_bwd_kernel(const VAParams P) {
   const int tile = G * kTileStride;
   float* att_s = reinterpret_cast<float*>(smem_raw) + warp * tile;
   float* s_s = reinterpret_cast<float*>(smem_raw) + (kWarps + warp) * tile;
-  uint32_t* row_s = reinterpret_cast<uint32_t*>(smem_raw + (size_t)2 * kWarps * tile * sizeof(float)) + warp * 32;
+  uint32_t* row_s = reinterpret_cast<uint32_t*>(smem_raw + (size_t)2 * kWarps * tile * sizeof(float)) + warp * 64;
+  uint32_t* orow_s = row_s + 32;             // destination row of dx (== row_s when scattering)
   float* gate_s = reinterpret_cast<float*>(smem_raw + (size_t)2 * kWarps * tile * sizeof(float) +
-                                           (size_t)kWarps * 32 * sizeof(uint32_t));  // [kWarps][2][G]
+                                           (size_t)kWarps * 64 * sizeof(uint32_t));  // [kWarps][2][G]
   const int sg = lane / LPR, lir = lane % LPR;
   const char* __restrict__ xb = reinterpret_cast<const char*>(P.x);
   const char* __restrict__ gob = reinterpret_cast<const char*>(P.gout);
@@ -337,12 +342,17 @@ view_attention_bwd_kernel(const VAParams P) {
   const bool single_tile = C <= TILE_C;
   const bool has_idx = P.idx != nullptr;
   const bool scatter = P.scatter && has_idx;
-  // How the per-(view,group) dot products are reduced across the lanes of a row:
-  //   cpg = 16-byte chunks per group when all groups are equally wide and chunk-aligned.
-  const int cpg = (C % G == 0 && (C / G) % VEC == 0) ? (C / G) / VEC : 0;
-  const bool cpg_pow2 = cpg > 0 && (cpg & (cpg - 1)) == 0;
-  const int red_mode = (cpg_pow2 && cpg <= LPR) ? 1 : ((cpg_pow2 && cpg % LPR == 0) ? 2 : 0);
-  const bool assign_s = single_tile && red_mode == 1;   // every (v,g) slot written exactly once
+  // cpg = chunks per group (host guarantees a power of two when REG); cpe = lanes of one row
+  // step that share a group; a (view,group) slot of s_s is written once per tile iff cpg <= LPR.
+  const int cpg = REG ? (C / G) / VEC : 0;
+  const int cpe = cpg < LPR ? cpg : LPR;
+  // CPL == 1 kernels always see the whole row in one tile and cpg <= LPR: plain assignment
+  const bool assign_s = (REG && CPL == 1) || (REG && single_tile && cpg <= LPR);
+  // butterfly step o contributes iff o < cpe: as a 0/1 multiplier (no predicates in the loop)
+  float red_mask[5];
+#pragma unroll
+  for (int b = 0; b < 5; ++b) red_mask[b] = ((1 << b) < cpe) ? 1.f : 0.f;
+  const bool leader = REG ? ((lir & (cpe - 1)) == 0) : (lir == 0);
 
   int gk0[CPL]; uint32_t off0[CPL]; bool live0[CPL];
 #pragma unroll
@@ -402,26 +412,31 @@ view_attention_bwd_kernel(const VAParams P) {
         att_s[slot] = expf((__ldg(cp + vs * G + e) - m) * inv_sq) * inv_den;
         if (!assign_s) s_s[slot] = 0.f;
       }
-      if (lane < nc)
-        row_s[lane] = has_idx ? (uint32_t)load_idx(P.idx, P.idx64, p0 + vs + lane)
-                              : (uint32_t)(p0 + vs + lane);
+      if (lane < nc) {
+        const uint32_t lin = (uint32_t)(p0 + vs + lane);
+        const uint32_t r = has_idx ? (uint32_t)load_idx(P.idx, P.idx64, p0 + vs + lane) : lin;
+        row_s[lane] = r;
+        orow_s[lane] = scatter ? r : lin;
+      }
       __syncwarp();
-      const uint32_t out_row0 = (uint32_t)(p0 + vs);
 
       for (int ct = 0; ct < C; ct += TILE_C) {
         if (!single_tile) load_gd(ct);
         const uint32_t* rs = row_s + sg;
+        const uint32_t* os = orow_s + sg;
         const float* as[CPL]; float* ss[CPL];
+        const char* xk[CPL]; char* ok_[CPL];     // per-lane base pointers: row address = 1 IMAD.WIDE
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
           as[k] = att_s + gk[k] * kTileStride + sg;
           ss[k] = s_s + gk[k] * kTileStride + sg;
+          xk[k] = xb + off[k];
+          ok_[k] = gxb + off[k];
         }
 
         // one row step: x chunk(s) of view v0+sg -> dx store + per-group dot product into s_s
-        auto consume = [&](int v0, const Chunk<T, VEC> (&f)[CPL], uint32_t srow, bool ok) {
-          const uint32_t orow = scatter ? srow : out_row0 + (uint32_t)(v0 + sg);
-          char* op = row_addr(gxb, orow, row_bytes);
+        auto consume = [&](int v0, const Chunk<T, VEC> (&f)[CPL], bool ok) {
+          const uint32_t orow = os[v0];
 #pragma unroll
           for (int k = 0; k < CPL; ++k) {
             float fv[VEC], dx[VEC];
@@ -434,18 +449,15 @@ view_attention_bwd_kernel(const VAParams P) {
               dx[j] = a * gd[k][j];
             }
             const bool lv = ok && live[k];
-            if (lv) store_chunk<T, VEC>(op + off[k], dx);
-            if (red_mode == 1) {              // groups = aligned blocks of cpg lanes
-              float r = dot;
-              for (int o = 1; o < cpg; o <<= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-              if (lv && (lir & (cpg - 1)) == 0) {
-                if (assign_s) ss[k][v0] = r; else ss[k][v0] += r;
-              }
-            } else if (red_mode == 2) {       // the whole row step lies in one group
+            if (lv) store_chunk<T, VEC>(row_addr(ok_[k], orow, row_bytes), dx);
+            if constexpr (REG) {              // groups = aligned blocks of cpe lanes
               float r = dot;
 #pragma unroll
-              for (int o = 1; o < LPR; o <<= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-              if (lv && lir == 0) ss[k][v0] += r;
+              for (int b = 0; (1 << b) < LPR; ++b)
+                r = fmaf(__shfl_xor_sync(0xffffffffu, r, 1 << b), red_mask[b], r);
+              if (lv && leader) {
+                if (assign_s) ss[k][v0] = r; else ss[k][v0] += r;
+              }
             } else {                          // irregular group sizes: one reduction per group
               for (int g = 0; g < G; ++g) {
                 const bool mine = lv && (gk[k] == g);
@@ -462,25 +474,22 @@ view_attention_bwd_kernel(const VAParams P) {
         int v0 = 0;
         for (; v0 + RPI * U <= nc; v0 += RPI * U) {
           Chunk<T, VEC> f[U][CPL];
-          uint32_t srow[U];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            srow[u] = rs[v0 + u * RPI];
-            const char* rp = row_addr(xb, srow[u], row_bytes);
+            const uint32_t srow = rs[v0 + u * RPI];
 #pragma unroll
-            for (int k = 0; k < CPL; ++k) f[u][k].load(rp + off[k]);
+            for (int k = 0; k < CPL; ++k) f[u][k].load(row_addr(xk[k], srow, row_bytes));
           }
 #pragma unroll
-          for (int u = 0; u < U; ++u) consume(v0 + u * RPI, f[u], srow[u], true);
+          for (int u = 0; u < U; ++u) consume(v0 + u * RPI, f[u], true);
         }
         for (; v0 < nc; v0 += RPI) {           // tail; idle sub-groups still join the shuffles
           const bool ok = v0 + sg < nc;
           Chunk<T, VEC> f[CPL];
           const uint32_t srow = ok ? rs[v0] : row_s[0];   // idle lanes re-read a valid row
-          const char* rp = row_addr(xb, srow, row_bytes);
 #pragma unroll
-          for (int k = 0; k < CPL; ++k) f[k].load(rp + off[k]);
-          consume(v0, f, srow, ok);
+          for (int k = 0; k < CPL; ++k) f[k].load(row_addr(xk[k], srow, row_bytes));
+          consume(v0, f, ok);
         }
         __syncwarp();
       }
@@ -540,10 +549,10 @@ __global__ void gate_reduce_kernel(const float* __restrict__ partial, float* __r
 // ---------------------------------------------------------------------------------------------
 // host dispatch
 // ---------------------------------------------------------------------------------------------
-struct VAConfig { int vec, lpr, cpl; };
+struct VAConfig { int vec, lpr, cpl; bool reg; };
 
 template <typename T>
-static VAConfig choose_config(const VAParams& P, const void* o1, const void* o2) {
+static VAConfig choose_config(const VAParams& P, const void* o1, const void* o2, bool need_regular) {
   constexpr int V16 = Vec16<T>::N;
   const int C = P.C, G = P.G;
   bool vec_ok = (C % V16 == 0) && aligned16(P.x) && aligned16(o1) && (o2 == nullptr || aligned16(o2));
@@ -551,10 +560,17 @@ static VAConfig choose_config(const VAParams& P, const void* o1, const void* o2)
     for (int c0 = 0; c0 < C && vec_ok; c0 += V16)
       if (group_of_channel(c0, C, G) != group_of_channel(c0 + V16 - 1, C, G)) vec_ok = false;
   }
+  // regular layout: equal groups made of a power-of-two number of chunks
+  auto regular = [&](int vec) {
+    if (C % G != 0 || (C / G) % vec != 0) return false;
+    const int cpg = (C / G) / vec;
+    return (cpg & (cpg - 1)) == 0;
+  };
+  if (vec_ok && need_regular && !regular(V16)) vec_ok = false;   // irregular: scalar bwd kernels
   VAConfig cfg;
-  if (!vec_ok) { cfg.vec = 1; cfg.lpr = 32; cfg.cpl = (C > 32) ? 4 : 1; return cfg; }
+  if (!vec_ok) { cfg.vec = 1; cfg.lpr = 32; cfg.cpl = (C > 32) ? 4 : 1; cfg.reg = regular(1); return cfg; }
   const int cv = C / V16;
-  cfg.vec = V16;
+  cfg.vec = V16; cfg.reg = true;
   if (cv <= 4) { cfg.lpr = 4; cfg.cpl = 1; }
   else if (cv <= 8) { cfg.lpr = 8; cfg.cpl = 1; }
   else if (cv <= 16) { cfg.lpr = 16; cfg.cpl = 1; }
@@ -584,7 +600,7 @@ static size_t fwd_smem(int G) {
   return (size_t)kWarps * G * kTileStride * sizeof(float) + (size_t)kWarps * 32 * sizeof(uint32_t);
 }
 static size_t bwd_smem(int G) {
-  return (size_t)2 * kWarps * G * kTileStride * sizeof(float) + (size_t)kWarps * 32 * sizeof(uint32_t) +
+  return (size_t)2 * kWarps * G * kTileStride * sizeof(float) + (size_t)kWarps * 64 * sizeof(uint32_t) +
          (size_t)kWarps * 2 * G * sizeof(float);
 }
 
@@ -597,15 +613,23 @@ static int launch_fwd(const VAParams& P, cudaStream_t st) {
   return check_launch("view_attention_fwd");
 }
 
-template <typename T, int VEC, int LPR, int CPL>
-static int launch_bwd(const VAParams& P, int* grid_out, cudaStream_t st) {
+template <typename T, int VEC, int LPR, int CPL, bool REG>
+static int launch_bwd_k(const VAParams& P, int* grid_out, cudaStream_t st) {
   const size_t smem = bwd_smem(P.G);
-  auto kern = view_attention_bwd_kernel<T, VEC, LPR, CPL, (CPL >= 4 ? 2 : kMinBlocksBwd)>;
+  auto kern = view_attention_bwd_kernel<T, VEC, LPR, CPL, (CPL >= 4 ? 2 : kMinBlocksBwd), REG>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int grid = va_grid(kern, smem, P.N);
   *grid_out = grid;
   kern<<<grid, kWarps * 32, smem, st>>>(P);
   return check_launch("view_attention_bwd");
+}
+
+template <typename T, int VEC, int LPR, int CPL>
+static int launch_bwd(const VAParams& P, bool reg, int* grid_out, cudaStream_t st) {
+  if constexpr (VEC == 1) {
+    if (!reg) return launch_bwd_k<T, VEC, LPR, CPL, false>(P, grid_out, st);
+  }
+  return launch_bwd_k<T, VEC, LPR, CPL, true>(P, grid_out, st);
 }
 
 #define DVA_VA_DISPATCH(FN, T, cfg, ...)                                                   \
@@ -624,12 +648,12 @@ static int launch_bwd(const VAParams& P, int* grid_out, cudaStream_t st) {
   } while (0)
 
 template <typename T> static int fwd_typed(const VAParams& P, cudaStream_t st) {
-  const VAConfig cfg = choose_config<T>(P, P.out, nullptr);
+  const VAConfig cfg = choose_config<T>(P, P.out, nullptr, false);
   DVA_VA_DISPATCH(launch_fwd, T, cfg, P, st);
 }
 template <typename T> static int bwd_typed(const VAParams& P, int* grid, cudaStream_t st) {
-  const VAConfig cfg = choose_config<T>(P, P.gout, P.gx);
-  DVA_VA_DISPATCH(launch_bwd, T, cfg, P, grid, st);
+  const VAConfig cfg = choose_config<T>(P, P.gout, P.gx, true);
+  DVA_VA_DISPATCH(launch_bwd, T, cfg, P, cfg.reg, grid, st);
 }
 
 static bool pow2_le32(int64_t g) { return g >= 1 && g <= 32 && (g & (g - 1)) == 0; }
