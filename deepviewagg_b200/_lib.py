@@ -10,7 +10,8 @@ import subprocess
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdva_b200.so")
+# DVA_B200_LIB: developer knob to load a tuning variant of the same library (bench sweeps)
+LIB_PATH = os.environ.get("DVA_B200_LIB") or os.path.join(_HERE, "libdva_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 DVA_OK, DVA_EINVAL, DVA_EALIGN, DVA_EUNSUPPORTED = 0, -1, -2, -3

@@ -38,8 +38,21 @@ struct VAParams {
   float eps;
 };
 
+#ifndef DVA_FWD_UNROLL
+#define DVA_FWD_UNROLL 8
+#endif
+#ifndef DVA_BWD_UNROLL
+#define DVA_BWD_UNROLL 4
+#endif
+#ifndef DVA_FWD_MINB
+#define DVA_FWD_MINB 4
+#endif
+#ifndef DVA_BWD_MINB
+#define DVA_BWD_MINB 4
+#endif
 constexpr int kWarps = 8;          // warps per CTA
-constexpr int kUnroll = 8;         // row loads in flight per lane (x CPL)
+constexpr int kUnroll = DVA_FWD_UNROLL;     // fwd: row loads in flight per lane (x CPL)
+constexpr int kUnrollBwd = DVA_BWD_UNROLL;  // bwd: row loads in flight per lane (x CPL)
 constexpr int kTileStride = 33;    // att tile is [G][33]: (g,v) -> bank (g+v)%32, conflict-free
 
 // A row chunk in flight: the raw 16 bytes (or one scalar) -- unpacked to fp32 only at use so
@@ -319,7 +332,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB)
 view_attention_bwd_kernel(const VAParams P) {
   constexpr int RPI = 32 / LPR;
   constexpr int TILE_C = VEC * LPR * CPL;
-  constexpr int U = (kUnroll / 2 / CPL) > 0 ? (kUnroll / 2 / CPL) : 1;
+  constexpr int U = (kUnrollBwd / CPL) > 0 ? (kUnrollBwd / CPL) : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = P.C, G = P.G;
@@ -593,8 +606,8 @@ static int va_grid(K kern, size_t smem, int64_t N) {
   return (int)blocks;
 }
 
-constexpr int kMinBlocksFwd = 4;   // 32 warps / SM
-constexpr int kMinBlocksBwd = 3;   // 24 warps / SM
+constexpr int kMinBlocksFwd = DVA_FWD_MINB;   // x 8 warps / SM
+constexpr int kMinBlocksBwd = DVA_BWD_MINB;
 
 static size_t fwd_smem(int G) {
   return (size_t)kWarps * G * kTileStride * sizeof(float) + (size_t)kWarps * 32 * sizeof(uint32_t);

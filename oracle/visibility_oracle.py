@@ -1,0 +1,171 @@
+"""ctypes wrapper of oracle/visibility_oracle.c plus numpy restatements of the integer CSR /
+lexicographic helpers (oracle; test infrastructure -- see oracle/__init__.py).
+
+  project_equirect / splat_boxes / zbuffer   <- visibility.py (numba CPU variants), see the .c file
+  pose_to_rotation_matrix                    <- visibility.py:57-90
+  lexargsort / lexargunique / lexunique      <- utils/multimodal.py:36-94, 289-323 (CPU/numpy path;
+                                                argsort made stable: the reference's np.argsort is
+                                                unstable, SURVEY.md D.15 -- ties are canonicalised)
+  csr_pointers / insert_empty_groups / index_select_pointers <- csr.py:158-264
+  image_mapping_from_dense                   <- image.py:1728-1795
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_build", "liboracle.so")
+_lib = None
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB):
+            subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
+        _lib = ctypes.CDLL(_LIB)
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def pose_to_rotation_matrix(opk):
+    """visibility.py:57-90, float32 like numba (cos/sin of float32 scalars, float32 products)."""
+    opk = np.asarray(opk, dtype=np.float32)
+    co, so, cp, sp, ck, sk = (np.cos(opk[0]), np.sin(opk[0]), np.cos(opk[1]), np.sin(opk[1]),
+                              np.cos(opk[2]), np.sin(opk[2]))
+    M_o = np.array([[1, 0, 0], [0, co, -so], [0, so, co]], dtype=np.float32)
+    M_p = np.array([[cp, 0, sp], [0, 1, 0], [-sp, 0, cp]], dtype=np.float32)
+    M_k = np.array([[ck, -sk, 0], [sk, ck, 0], [0, 0, 1]], dtype=np.float32)
+    return np.dot(M_o, np.dot(M_p, M_k)).astype(np.float32)
+
+
+def project_equirect(xyz, img_xyz, rotation, W, H, crop_top=0, crop_bottom=0, r_min=0.5, r_max=30.0):
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    n = xyz.shape[0]
+    dist = np.empty(n, np.float32)
+    xp, yp = np.empty(n, np.float64), np.empty(n, np.float64)
+    keep = np.empty(n, np.uint8)
+    R = np.ascontiguousarray(rotation, dtype=np.float32).reshape(-1)
+    c = np.ascontiguousarray(img_xyz, dtype=np.float32)
+    _load().oracle_project_equirect(_p(xyz), _p(c), _p(R), ctypes.c_int64(n), W, H, crop_top, crop_bottom,
+                                    ctypes.c_float(r_min), ctypes.c_float(r_max), _p(dist), _p(xp), _p(yp),
+                                    _p(keep))
+    return dist, xp, yp, keep.astype(bool)
+
+
+def splat_boxes(x_proj, y_proj, dist, W, H, crop_top=0, crop_bottom=0, voxel=0.02, k_swell=1.0,
+                d_swell=1000.0, camera="equirectangular", fx=0.0, fy=0.0):
+    xp = np.ascontiguousarray(x_proj, np.float64)
+    yp = np.ascontiguousarray(y_proj, np.float64)
+    d = np.ascontiguousarray(dist, np.float32)
+    m = xp.shape[0]
+    out = np.empty((m, 4), np.int32)
+    D = ctypes.c_double
+    if camera == "equirectangular":
+        _load().oracle_splat_equirect(_p(xp), _p(yp), _p(d), ctypes.c_int64(m), W, H, crop_top, crop_bottom,
+                                      D(voxel), D(k_swell), D(d_swell), _p(out))
+    else:
+        _load().oracle_splat_pinhole(_p(xp), _p(yp), _p(d), ctypes.c_int64(m), W, H, crop_top, crop_bottom,
+                                     D(voxel), D(k_swell), D(d_swell), D(fx), D(fy), _p(out))
+    return out
+
+
+def zbuffer(splat, dist, x_proj, y_proj, W, H, crop_top=0, crop_bottom=0, exact=False):
+    """-> (indices, x_pix, y_pix) in the reference's np.where order (row-major over [x, y])."""
+    sp = np.ascontiguousarray(splat, np.int32)
+    d = np.ascontiguousarray(dist, np.float32)
+    xp = np.ascontiguousarray(x_proj, np.float64)
+    yp = np.ascontiguousarray(y_proj, np.float64)
+    m = sp.shape[0]
+    Hc = H - crop_top - crop_bottom
+    idx_map = np.empty((W, Hc), np.int64)
+    _load().oracle_zbuffer(_p(sp), _p(d), _p(xp), _p(yp), ctypes.c_int64(m), W, H, crop_top, crop_bottom,
+                           int(bool(exact)), _p(idx_map))
+    x_pix, y_pix = np.where(idx_map != -1)
+    return idx_map[x_pix, y_pix], x_pix, y_pix + crop_top, idx_map
+
+
+# ---- lexicographic helpers (utils/multimodal.py) ---------------------------------------------------
+def _composite(*arrays):
+    """CompositeNDArray (utils/multimodal.py:175-250): key = sum a_i * prod_{j>i} (max_j + 1)."""
+    arrays = [np.asarray(a).astype(np.int64) for a in arrays]
+    if arrays[0].shape[0] == 0:
+        return np.zeros(0, np.int64), [1] * len(arrays)
+    maxs = [int(np.abs(a).max()) + 1 for a in arrays]
+    bases = [int(np.prod(maxs[i + 1:])) for i in range(len(arrays) - 1)] + [1]
+    return sum(a * b for a, b in zip(arrays, bases)), bases
+
+
+def lexargsort(*arrays):
+    key, _ = _composite(*arrays)
+    return np.argsort(key, kind="stable")
+
+
+def lexargunique(*arrays):
+    key, _ = _composite(*arrays)
+    return np.unique(key, return_index=True)[1]
+
+
+def lexunique(*arrays):
+    key, bases = _composite(*arrays)
+    u = np.unique(key)
+    out = []
+    for b in bases:
+        out.append(u // b)
+        u = u % b
+    return out
+
+
+# ---- CSR containers (csr.py) ---------------------------------------------------------------------------
+def csr_pointers(sorted_ids):
+    """_sorted_indices_to_pointers, csr.py:158-172."""
+    ids = np.asarray(sorted_ids)
+    return np.concatenate([[0], np.where(ids[1:] > ids[:-1])[0] + 1, [ids.shape[0]]]).astype(np.int64)
+
+
+def insert_empty_groups(pointers, group_indices, num_groups=None):
+    """csr.py:197-229: pointers.repeat_interleave(ends - starts)."""
+    gi = np.asarray(group_indices).astype(np.int64)
+    ng = int(gi.max()) + 1 if num_groups is None else max(int(gi.max()) + 1, int(num_groups))
+    starts = np.concatenate([[-1], gi])
+    ends = np.concatenate([gi, [ng]])
+    return np.repeat(np.asarray(pointers), ends - starts)
+
+
+def pointers_from_sorted_with_empties(sorted_ids, num_groups):
+    ids = np.asarray(sorted_ids)
+    p = csr_pointers(ids)
+    return insert_empty_groups(p, ids[p[1:] - 1], num_groups)
+
+
+def index_select_pointers(pointers, indices):
+    """csr.py:235-264 -> (pointers_new, val_idx)."""
+    pointers, indices = np.asarray(pointers), np.asarray(indices)
+    sizes = pointers[indices + 1] - pointers[indices]
+    pn = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    val = np.arange(pn[-1]) - np.repeat(pn[:-1], sizes) + np.repeat(pointers[indices], sizes)
+    return pn, val.astype(np.int64)
+
+
+def image_mapping_from_dense(point_ids, image_ids, pixels, features, num_points):
+    """ImageMapping.from_dense, image.py:1728-1795 (stable sort; see module docstring)."""
+    order = lexargsort(point_ids, image_ids)
+    pid, iid, pix = np.asarray(point_ids)[order], np.asarray(image_ids)[order], np.asarray(pixels)[order]
+    feat = None if features is None else np.asarray(features)[order]
+    key, _ = _composite(pid, iid)
+    atomic_ptr = csr_pointers(key)
+    last = atomic_ptr[1:] - 1
+    iid_v, pid_v = iid[last], pid[last]
+    if feat is not None:
+        counts = np.diff(atomic_ptr)
+        sums = np.add.reduceat(feat.astype(np.float32), atomic_ptr[:-1], axis=0)
+        feat = (sums / np.maximum(counts, 1)[:, None]).astype(np.float32)
+    ptr = csr_pointers(pid_v)
+    n = max(int(num_points), int(pid_v.max()) + 1)
+    ptr = insert_empty_groups(ptr, pid_v[ptr[1:] - 1], n)
+    return dict(pointers=ptr, images=iid_v, atomic_pointers=atomic_ptr, pixels=pix, features=feat)

@@ -1,0 +1,65 @@
+"""N>1 host logic on CPU: world_size 2, gloo.  Scene sharding, the single bucketed gradient
+all-reduce and the max-over-ranks timing rule that bench.py relies on."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from deepviewagg_b200 import distributed as D
+    from deepviewagg_b200.modules.multimodal.pooling import GroupBimodalCSRPool
+    # identical replicas (same seed), different "scenes" per rank -> different gradients
+    torch.manual_seed(0)
+    m = GroupBimodalCSRPool(in_map=8, in_mod=16, num_groups=4, use_num=True)
+    shard = D.shard_indices(7, rank, world)
+    gen = torch.Generator().manual_seed(100 + rank)
+    for p in m.parameters():
+        p.grad = torch.randn(p.shape, generator=gen)
+    local = [p.grad.clone() for p in m.parameters()]
+    n = D.allreduce_gradients(m.parameters(), average=True)
+    t = D.max_over_ranks(1.0 + rank)
+    s = D.sum_over_ranks(10.0)
+    q.put((rank, shard, n, t, s, local, [p.grad.clone() for p in m.parameters()]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_and_grad_allreduce():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, s0, n0, t0, sum0, l0, g0), (r1, s1, n1, t1, sum1, l1, g1) = res
+    assert sorted(s0 + s1) == list(range(7)) and not set(s0) & set(s1)   # disjoint cover
+    assert s0 == [0, 2, 4, 6] and s1 == [1, 3, 5]
+    assert n0 == n1 == sum(g.numel() for g in g0) > 0                       # one bucket, all grads
+    assert t0 == t1 == 2.0 and sum0 == sum1 == 20.0                         # max / sum over ranks
+    for a, b, x, y in zip(l0, l1, g0, g1):
+        assert torch.allclose(x, (a + b) / 2, atol=1e-6) and torch.equal(x, y)
+
+
+def test_single_process_is_a_noop():
+    from deepviewagg_b200 import distributed as D
+    p = torch.nn.Parameter(torch.ones(3))
+    p.grad = torch.full((3,), 2.0)
+    assert D.allreduce_gradients([p]) == 0 and D.max_over_ranks(3.5) == 3.5
+    assert D.shard_indices(5, 0, 1) == [0, 1, 2, 3, 4]

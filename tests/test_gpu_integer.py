@@ -1,0 +1,105 @@
+"""GPU parity of the integer kernels (projection / splat boxes / z-buffer / CSR bookkeeping)
+against fixtures of the executed numba reference and against the C oracle.  Bit-exact."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import visibility_oracle as VO
+
+pytestmark = pytest.mark.gpu
+
+
+def _np(t):
+    return t.cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+
+
+@pytest.mark.parametrize("tag", ["nocrop", "crop"])
+def test_visibility_pipeline_vs_numba_fixture(tag):
+    from deepviewagg_b200.core.multimodal import visibility as V
+    g = load_golden("zbuffer_" + tag)
+    W, H = [int(v) for v in g["size"]]
+    ct, cb = [int(v) for v in g["crop"]]
+    r_min, r_max = [float(v) for v in g["r"]]
+    assert torch.equal(V.pose_to_rotation_matrix(g["img_opk"]), g["rotation"])
+    idx, dist, xp, yp = V.camera_projection(g["xyz"].cuda(), g["img_xyz"], img_opk=g["img_opk"], img_size=(W, H),
+                                            crop_top=ct, crop_bottom=cb, r_max=r_max, r_min=r_min)
+    assert torch.equal(idx.cpu(), g["proj_idx"])                       # same kept set
+    assert torch.equal(dist.cpu(), g["dist"])                          # float32 distances bit-exact
+    px_eq = (xp.cpu().floor() == g["x_proj"].floor()) & (yp.cpu().floor() == g["y_proj"].floor())
+    assert px_eq.double().mean() > 0.9995                               # float projection: pixel-equality rate
+    assert (xp.cpu() - g["x_proj"]).abs().max() < 1e-3
+    # integer stages on the reference's own projections: bit-exact
+    xr, yr, dr = g["x_proj"].cuda(), g["y_proj"].cuda(), g["dist"].cuda()
+    sp = V.splat_boxes(xr, yr, dr, None, (W, H), ct, cb, voxel=0.05, k_swell=1.0, d_swell=1000)
+    assert torch.equal(sp.cpu(), g["splat"].int())
+    for exact in (0, 1):
+        i2, x2, y2 = V.visibility_from_splatting(xr, yr, dr, None, img_size=(W, H), crop_top=ct, crop_bottom=cb,
+                                                 voxel=0.05, k_swell=1.0, d_swell=1000, exact=bool(exact))
+        assert torch.equal(i2.cpu(), g[f"vis_idx_{exact}"])
+        assert torch.equal(x2.cpu(), g[f"vis_x_{exact}"])
+        assert torch.equal(y2.cpu(), g[f"vis_y_{exact}"])
+    # whole model object (projection + z-buffer + features) runs and is self-consistent
+    model = V.SplattingVisibility(voxel=0.05, exact=True, img_size=(W, H), crop_top=ct, crop_bottom=cb,
+                                  r_max=r_max, r_min=r_min)
+    out = model(g["xyz"].cuda(), g["img_xyz"], img_opk=g["img_opk"], normals=torch.nn.functional.normalize(
+        g["xyz"], dim=1).cuda())
+    assert out["idx"].shape == out["x"].shape == out["y"].shape == out["depth"].shape
+    assert out["features"].shape == (out["idx"].shape[0], 3)
+
+
+def test_pinhole_splat_vs_numba_fixture():
+    from deepviewagg_b200.core.multimodal import visibility as V
+    g = load_golden("splat_pinhole")
+    W, H = [int(v) for v in g["size"]]
+    intr = [[float(g["fx"]), 0, 0], [0, float(g["fy"]), 0]]
+    sp = V.splat_boxes(g["x_proj"].cuda(), g["y_proj"].cuda(), g["dist"].cuda(), intr, (W, H), voxel=0.03,
+                       k_swell=1.0, d_swell=1000, camera="scannet")
+    assert torch.equal(sp.cpu(), g["splat"].int())
+
+
+def test_zbuffer_large_random_vs_c_oracle():
+    """1M points on a 2048x1024 equirectangular image (the BASELINE splat case), ties included."""
+    from deepviewagg_b200.core.multimodal import visibility as V
+    rng = np.random.default_rng(0)
+    m, W, H = 1_000_000, 2048, 1024
+    xp = rng.uniform(0, W, m)
+    yp = rng.uniform(20, H - 20, m)
+    dist = rng.uniform(0.6, 20, m).astype(np.float32)
+    tie = np.arange(0, m - 7, 7)
+    dist[tie] = dist[tie + 3]                                     # exact depth ties -> lowest index wins
+    sp = VO.splat_boxes(xp, yp, dist, W, H, 8, 8, voxel=0.05)
+    sg = V.splat_boxes(torch.from_numpy(xp).cuda(), torch.from_numpy(yp).cuda(), torch.from_numpy(dist).cuda(),
+                       None, (W, H), 8, 8, voxel=0.05)
+    assert np.array_equal(_np(sg), sp)
+    for exact in (False, True):
+        i_ref, x_ref, y_ref, _ = VO.zbuffer(sp, dist, xp, yp, W, H, 8, 8, exact=exact)
+        i2, x2, y2 = V.visibility_from_splatting(torch.from_numpy(xp).cuda(), torch.from_numpy(yp).cuda(),
+                                                 torch.from_numpy(dist).cuda(), None, img_size=(W, H), crop_top=8,
+                                                 crop_bottom=8, voxel=0.05, exact=exact)
+        assert np.array_equal(_np(i2), i_ref) and np.array_equal(_np(x2), x_ref) and np.array_equal(_np(y2), y_ref)
+
+
+def test_csr_kernels_vs_oracle():
+    from deepviewagg_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(1)
+    for n, ng in ((0, 5), (1, 1), (5000, 700), (100000, 100000), (10, 1000)):
+        ids = np.sort(rng.integers(0, ng, n)).astype(np.int64)
+        ref = VO.pointers_from_sorted_with_empties(ids, ng) if n else np.zeros(ng + 1, np.int64)
+        d_ids = torch.from_numpy(ids).cuda()
+        ptr = torch.full((ng + 1,), -7, dtype=torch.int64, device="cuda")
+        _lib.check(lib.dva_csr_pointers_from_sorted(_lib.ptr(d_ids), _lib.ptr(ptr), n, ng, _lib.stream_ptr()), "csr")
+        assert np.array_equal(_np(ptr), ref), (n, ng)
+    g = load_golden("image_mapping")
+    pointers, sel = g["pointers"], g["sel"]
+    pn_ref, val_ref = VO.index_select_pointers(_np(pointers), _np(sel))
+    assert np.array_equal(pn_ref, _np(g["sel_pointers"]))
+    val = torch.empty(int(pn_ref[-1]), dtype=torch.int64, device="cuda")
+    d_ptr, d_sel, d_pn = pointers.cuda(), sel.cuda(), torch.from_numpy(pn_ref).cuda()  # keep alive
+    _lib.check(lib.dva_csr_select_values(_lib.ptr(d_ptr), _lib.ptr(d_sel), _lib.ptr(d_pn), _lib.ptr(val),
+                                         sel.numel(), val.numel(), _lib.stream_ptr()), "select")
+    assert np.array_equal(_np(val), val_ref)
+    assert torch.equal(g["images"][val.cpu()], g["sel_images"])
