@@ -32,7 +32,9 @@ def _worker(rank, world, port, q):
     n = D.allreduce_gradients(m.parameters(), average=True)
     t = D.max_over_ranks(1.0 + rank)
     s = D.sum_over_ranks(10.0)
-    q.put((rank, shard, n, t, s, local, [p.grad.clone() for p in m.parameters()]))
+    # plain python lists: tensors in a Queue are shared through fds that die with the sender
+    q.put((rank, shard, n, t, s, [g.reshape(-1).tolist() for g in local],
+           [p.grad.reshape(-1).tolist() for p in m.parameters()]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -51,9 +53,10 @@ def test_two_rank_sharding_and_grad_allreduce():
     (r0, s0, n0, t0, sum0, l0, g0), (r1, s1, n1, t1, sum1, l1, g1) = res
     assert sorted(s0 + s1) == list(range(7)) and not set(s0) & set(s1)   # disjoint cover
     assert s0 == [0, 2, 4, 6] and s1 == [1, 3, 5]
-    assert n0 == n1 == sum(g.numel() for g in g0) > 0                       # one bucket, all grads
+    assert n0 == n1 == sum(len(g) for g in g0) > 0                          # one bucket, all grads
     assert t0 == t1 == 2.0 and sum0 == sum1 == 20.0                         # max / sum over ranks
     for a, b, x, y in zip(l0, l1, g0, g1):
+        a, b, x, y = (torch.tensor(v) for v in (a, b, x, y))
         assert torch.allclose(x, (a + b) / 2, atol=1e-6) and torch.equal(x, y)
 
 
