@@ -189,6 +189,68 @@ def main():
     save("simple_pools", **arrays)
 
     make_integer_golden(ref)
+    make_branch_golden(ref)
+
+
+def toy_settings(gen, n_points, specs, F=8):
+    """Dense (point, image, pixel, feature) mappings per setting: one pixel per view ('exact'
+    splatting, the only mode the shipped configs use)."""
+    out = []
+    for (W, H, n_img, mean_v) in specs:
+        counts = torch.poisson(torch.full((n_points,), float(mean_v)), generator=gen).clamp(0, n_img).long()
+        pid = torch.arange(n_points).repeat_interleave(counts)
+        iid = torch.cat([torch.randperm(n_img, generator=gen)[:int(c)] for c in counts]) if pid.numel() else pid
+        pix = torch.stack([torch.randint(0, W, (pid.numel(),), generator=gen),
+                           torch.randint(0, H, (pid.numel(),), generator=gen)], 1).short()
+        feat = torch.rand(pid.numel(), F, generator=gen)
+        out.append(dict(W=W, H=H, n_img=n_img, pid=pid, iid=iid, pix=pix, feat=feat))
+    return out
+
+
+def make_branch_golden(ref):
+    """config #0 ("toy: 1k points x 4 views, CPU forward through the DeepViewAgg module"): the
+    reference's UnimodalBranch (modules.py:249-566) on a two-setting ImageData, atomic max pool,
+    GroupBimodalCSRPool view pool, concatenation fusion; forward + gradients."""
+    import numpy as np
+    P, I, M = ref.pooling, ref.image, ref.modules
+    gen = torch.Generator().manual_seed(4242)
+    torch.manual_seed(4242)
+    N, C3, C = 1000, 12, 16
+    specs = [(64, 32, 3, 2.2), (48, 48, 2, 1.6)]
+    xs_shape = [(3, C, 16, 32), (2, C, 48, 48)]          # setting 0 at half resolution (downscale 2)
+    settings = toy_settings(gen, N, specs)
+    ims, xs, arrays = [], [], {}
+    for s, (st, shp) in enumerate(zip(settings, xs_shape)):
+        im = I.SameSettingImageData(path=np.array([f"img_{s}_{i}" for i in range(st["n_img"])]),
+                                    pos=torch.zeros(st["n_img"], 3), opk=torch.zeros(st["n_img"], 3),
+                                    ref_size=(st["W"], st["H"]), proj_upscale=1, downscale=1)
+        im.mappings = I.ImageMapping.from_dense(st["pid"], st["iid"], st["pix"], st["feat"], num_points=N)
+        x = torch.randn(shp, generator=gen).relu().requires_grad_(True)
+        im.x = x
+        ims.append(im)
+        xs.append(x)
+        for k in ("pid", "iid", "pix", "feat"):
+            arrays[f"s{s}_{k}"] = st[k]
+        arrays[f"s{s}_x"] = x
+        arrays[f"s{s}_size"] = np.array([st["W"], st["H"], st["n_img"]])
+    mod = I.ImageData(ims)
+    view_pool = P.GroupBimodalCSRPool(in_map=8, in_mod=C, num_groups=4, use_num=True)
+    with torch.no_grad():
+        for k, p in view_pool.named_parameters():
+            if "batch_norm" in k or k.startswith("G."):
+                p.add_(0.3 * torch.randn(p.shape, generator=gen))
+    branch = M.UnimodalBranch(None, P.BimodalCSRPool(mode="max"), view_pool, ref.fusion.BimodalFusion("concatenation"))
+    branch.train()
+    x_3d = torch.randn(N, C3, generator=gen).requires_grad_(True)
+    w = torch.randn(N, C3 + C, generator=gen)
+    sd0 = {"sd/" + k: v.clone() for k, v in view_pool.state_dict().items()}
+    out = branch({"x_3d": x_3d, "x_seen": None, "modalities": {"image": mod}}, "image")
+    params = dict(view_pool.named_parameters())
+    gs = torch.autograd.grad((out["x_3d"] * w).sum(), [x_3d] + xs + list(params.values()), allow_unused=True)
+    names = ["x_3d", "s0_x", "s1_x"] + ["param/" + k for k in params]
+    grads = {"grad/" + n: (g if g is not None else torch.zeros(1)) for n, g in zip(names, gs)}
+    save("unimodal_branch_toy", x_3d=x_3d, w=w, out=out["x_3d"], x_seen=out["x_seen"],
+         csr=mod.view_cat_csr_indexing, n_points=np.array(N), **arrays, **sd0, **grads)
 
 
 def make_integer_golden(ref):

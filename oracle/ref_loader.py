@@ -90,5 +90,19 @@ def load_reference(with_visibility=True):
                           "torch_points3d/core/multimodal/visibility.py")
     mm.visibility = ns.visibility
     ns.image = _load("torch_points3d.core.multimodal.image", "torch_points3d/core/multimodal/image.py")
+    # modules.py: needs MODALITY_NAMES (core/multimodal/data.py:9-10, torch_geometric-free stub),
+    # ModalityDropout and a torchsparse stub (hard import at modules.py:10; unused on dense tensors)
+    data_stub = _stub("torch_points3d.core.multimodal.data")
+    data_stub.MODALITY_NAMES = ["image"]
+    tsp = _stub("torchsparse")
+    tsp_nn = _stub("torchsparse.nn")
+    tsp_f = _stub("torchsparse.nn.functional")
+    tsp_f.sphash = tsp_f.sphashquery = None
+    tsp.nn, tsp_nn.functional = tsp_nn, tsp_f
+    tsp.SparseTensor = type("SparseTensor", (), {})
+    ns.dropout = _load("torch_points3d.modules.multimodal.dropout",
+                       "torch_points3d/modules/multimodal/dropout.py")
+    ns.modules = _load("torch_points3d.modules.multimodal.modules",
+                       "torch_points3d/modules/multimodal/modules.py")
     _loaded = ns
     return ns

@@ -1,0 +1,88 @@
+"""config #0 (toy: 1k points x ~4 views through the DeepViewAgg module): our UnimodalBranch on the
+GPU vs the reference's UnimodalBranch executed on CPU (tests/golden/unimodal_branch_toy.npz):
+output features, seen mask, gradients w.r.t. the 3D features, the 2D feature maps and every
+view-pool parameter.  Also the container kernels on CUDA tensors."""
+import pytest
+import torch
+
+from conftest import load_golden
+from test_containers import _toy_image_data, canon_pixels
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(a, b, tol, what):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    err = float((a - b).abs().max()) / max(float(b.abs().max()), 1e-30)
+    assert err <= tol, f"{what}: rel err {err:.3e} > {tol}"
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_unimodal_branch_vs_reference(channels_last):
+    from deepviewagg_b200.modules.multimodal.fusion import BimodalFusion
+    from deepviewagg_b200.modules.multimodal.modules import UnimodalBranch
+    from deepviewagg_b200.modules.multimodal.pooling import BimodalCSRPool, GroupBimodalCSRPool
+    g = load_golden("unimodal_branch_toy")
+    mod = _toy_image_data(g, "cuda")
+    xs = []
+    for im in mod:
+        x = im.x.detach().clone()
+        if channels_last:
+            x = x.contiguous(memory_format=torch.channels_last)
+        x.requires_grad_(True)
+        im._x = x
+        xs.append(x)
+    view_pool = GroupBimodalCSRPool(in_map=8, in_mod=16, num_groups=4, use_num=True)
+    view_pool.load_state_dict(g["sd"], strict=True)
+    branch = UnimodalBranch(None, BimodalCSRPool(mode="max"), view_pool, BimodalFusion("concatenation")).cuda()
+    branch.train()
+    x_3d = g["x_3d"].cuda().requires_grad_(True)
+    out = branch({"x_3d": x_3d, "x_seen": None, "modalities": {"image": mod}}, "image")
+    assert branch.out_channels == 28
+    _close(out["x_3d"], g["out"], 1e-4, "x_3d out")
+    assert torch.equal(out["x_seen"].cpu(), g["x_seen"])
+    params = dict(view_pool.named_parameters())
+    grads = torch.autograd.grad((out["x_3d"] * g["w"].cuda()).sum(), [x_3d] + xs + list(params.values()),
+                                allow_unused=True)
+    names = ["x_3d", "s0_x", "s1_x"] + ["param/" + k for k in params]
+    for n, gr in zip(names, grads):
+        ref = g["grad"][n]
+        if gr is None:
+            assert float(ref.abs().max()) == 0, n
+            continue
+        assert (gr.cpu() - ref).abs().max() <= 2e-4 * max(1.0, float(ref.abs().max())), n
+
+
+def test_branch_empty_modality_and_identity():
+    from deepviewagg_b200.modules.multimodal.fusion import BimodalFusion
+    from deepviewagg_b200.modules.multimodal.modules import IdentityBranch, MultimodalBlockDown, UnimodalBranch
+    from deepviewagg_b200.modules.multimodal.pooling import BimodalCSRPool
+    from deepviewagg_b200.core.multimodal.image import ImageData
+    branch = UnimodalBranch(None, BimodalCSRPool("max"), BimodalCSRPool("mean"), BimodalFusion("concatenation"),
+                            out_channels=20).cuda()
+    x_3d = torch.randn(7, 12, device="cuda")
+    d = branch({"x_3d": x_3d, "x_seen": None, "modalities": {"image": ImageData([])}}, "image")
+    assert d["x_3d"].shape == (7, 20) and (d["x_3d"][:, 12:] == 0).all() and d["x_seen"] is None
+    blk = MultimodalBlockDown(None, None, image=IdentityBranch())
+    d2 = {"x_3d": x_3d, "x_seen": None, "modalities": {}}
+    assert blk(d2) is d2
+
+
+def test_containers_on_cuda_match_cpu():
+    from deepviewagg_b200.core.multimodal.image import ImageMapping
+    g = load_golden("image_mapping")
+    args = [g[k] for k in ("point_ids", "image_ids", "pixels", "features")]
+    m_cpu = ImageMapping.from_dense(*args, num_points=int(g["num_points"]))
+    m = ImageMapping.from_dense(*[a.cuda() for a in args], num_points=int(g["num_points"]))
+    assert torch.equal(m.pointers.cpu(), g["pointers"]) and torch.equal(m.images.cpu(), g["images"])
+    assert torch.equal(m.atomic_csr_indexing.cpu(), g["atomic_pointers"])
+    assert torch.allclose(m.features.cpu(), g["out_features"], atol=1e-6)
+    ms = m.select_points(g["sel"].cuda(), mode="pick")
+    assert torch.equal(ms.pointers.cpu(), g["sel_pointers"]) and torch.equal(ms.images.cpu(), g["sel_images"])
+    gm = load_golden("image_mapping_merge")
+    mg = m.select_points(gm["merge_idx"].cuda(), mode="merge")
+    assert torch.equal(mg.pointers.cpu(), gm["pointers"]) and torch.equal(mg.images.cpu(), gm["images"])
+    assert torch.equal(canon_pixels(mg.pixels.cpu(), mg.atomic_csr_indexing.cpu()),
+                       canon_pixels(gm["pixels"], gm["atomic_pointers"]))
+    assert torch.allclose(mg.features.cpu(), gm["features"], atol=1e-6)
+    assert torch.equal(m_cpu.pixels, m.pixels.cpu())
