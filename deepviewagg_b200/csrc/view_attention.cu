@@ -60,11 +60,13 @@ constexpr int kTileStride = 33;    // att tile is [G][33]: (g,v) -> bank (g+v)%3
 template <typename T, int VEC> struct Chunk {
   uint4 raw;
   __device__ __forceinline__ void load(const void* p) { raw = ldg_stream16(p); }
+  __device__ __forceinline__ void zero() { raw = make_uint4(0u, 0u, 0u, 0u); }
   __device__ __forceinline__ void get(float (&f)[VEC]) const { unpack16<T, VEC>(raw, f); }
 };
 template <typename T> struct Chunk<T, 1> {
   T raw;
   __device__ __forceinline__ void load(const void* p) { raw = __ldg(reinterpret_cast<const T*>(p)); }
+  __device__ __forceinline__ void zero() { raw = Cvt<T>::from_f(0.f); }
   __device__ __forceinline__ void get(float (&f)[1]) const { f[0] = Cvt<T>::to_f(raw); }
 };
 template <typename T, int VEC>
@@ -269,15 +271,29 @@ view_attention_fwd_kernel(const VAParams P) {
             }
           }
         }
-        // ---- tail: one row step at a time
-        for (; v0 < nc; v0 += RPI) {
-          if (v0 + sg < nc) {
-            const uint32_t srow = rs[v0];
+        // ---- tail: the remaining < U row steps, all loads issued before the first use
+        if (v0 < nc) {
+          Chunk<T, VEC> f[U][CPL];
+          bool ok[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            ok[u] = v0 + u * RPI + sg < nc;
+            if (v0 + u * RPI < nc) {           // warp-uniform: skip whole row steps past the end
+              const uint32_t srow = rs[ok[u] ? v0 + u * RPI : 0 - sg];   // idle sub-group: row 0
+#pragma unroll
+              for (int k = 0; k < CPL; ++k) f[u][k].load(row_addr(xk[k], srow, row_bytes));
+            } else {
+#pragma unroll
+              for (int k = 0; k < CPL; ++k) f[u][k].zero();
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
 #pragma unroll
             for (int k = 0; k < CPL; ++k) {
               float fv[VEC];
-              load_chunk<T, VEC>(row_addr(xk[k], srow, row_bytes), fv);
-              const float a = as[k][v0];
+              f[u][k].get(fv);
+              const float a = ok[u] ? as[k][v0 + u * RPI] : 0.f;
 #pragma unroll
               for (int j = 0; j < VEC; ++j) acc[k][j] = fmaf(a, fv[j], acc[k][j]);
             }
@@ -333,6 +349,7 @@ view_attention_bwd_kernel(const VAParams P) {
   constexpr int RPI = 32 / LPR;
   constexpr int TILE_C = VEC * LPR * CPL;
   constexpr int U = (kUnrollBwd / CPL) > 0 ? (kUnrollBwd / CPL) : 1;
+  constexpr int UT = U >= 2 ? 2 : 1;          // tail block width
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = P.C, G = P.G;
@@ -484,6 +501,7 @@ view_attention_bwd_kernel(const VAParams P) {
           }
         };
 
+        // main loop: U full row steps, all loads issued before the first use, no predicates
         int v0 = 0;
         for (; v0 + RPI * U <= nc; v0 += RPI * U) {
           Chunk<T, VEC> f[U][CPL];
@@ -496,13 +514,23 @@ view_attention_bwd_kernel(const VAParams P) {
 #pragma unroll
           for (int u = 0; u < U; ++u) consume(v0 + u * RPI, f[u], true);
         }
-        for (; v0 < nc; v0 += RPI) {           // tail; idle sub-groups still join the shuffles
-          const bool ok = v0 + sg < nc;
-          Chunk<T, VEC> f[CPL];
-          const uint32_t srow = ok ? rs[v0] : row_s[0];   // idle lanes re-read a valid row
+        // tail: predicated blocks of UT row steps (kept narrow: a U-wide tail spills at 64 registers);
+        // idle sub-groups still join the shuffles of consume()
+        for (; v0 < nc; v0 += RPI * UT) {
+          Chunk<T, VEC> f[UT][CPL];
+          bool okv[UT];
 #pragma unroll
-          for (int k = 0; k < CPL; ++k) f[k].load(row_addr(xk[k], srow, row_bytes));
-          consume(v0, f, ok);
+          for (int u = 0; u < UT; ++u) {
+            okv[u] = v0 + u * RPI + sg < nc;
+            if (v0 + u * RPI < nc) {           // warp-uniform
+              const uint32_t srow = okv[u] ? rs[v0 + u * RPI] : row_s[0];   // idle sub-group: a valid row
+#pragma unroll
+              for (int k = 0; k < CPL; ++k) f[u][k].load(row_addr(xk[k], srow, row_bytes));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < UT; ++u)
+            if (v0 + u * RPI < nc) consume(okv[u] ? v0 + u * RPI : 0 - sg, f[u], okv[u]);   // warp-uniform guard
         }
         __syncwarp();
       }
