@@ -50,8 +50,11 @@ SIGNATURES = {
                                  _i32, _vp]),
     "dva_splat_boxes": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _f64, _f64, _f64,
                                _i32, _f64, _f64, _vp]),
+    "dva_splat_boxes_from_width": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp]),
     "dva_project_equirectangular": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64,
                                            _i64, _f32, _f32, _vp]),
+    "dva_project_camera": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _f32,
+                                  _f32, _vp]),
     "dva_csr_pointers_from_sorted": (_i32, [_vp, _vp, _i64, _i64, _vp]),
     "dva_csr_select_values": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp]),
 }

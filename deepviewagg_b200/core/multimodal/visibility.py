@@ -4,13 +4,13 @@ variants, which are the authoritative ones (its README.md:122-123 warns against 
 mapping path): integer outputs -- splat boxes, z-buffer winners, pixel coordinates -- are
 bit-identical to the numba loops given the same projections.
 
-  camera_projection          <- visibility.py:478-538, 592-623   (s3dis_equirectangular)
+  camera_projection          <- visibility.py:478-538, 592-623   (equirectangular, pinhole, fisheye)
   visibility_from_splatting  <- visibility.py:1073-1195, 1288-1322
   postprocess_features       <- visibility.py:1548-1582
   VisibilityModel, SplattingVisibility <- visibility.py:1677-1776
 
-Kernels: csrc/zbuffer.cu through the C ABI (dva_project_equirectangular, dva_splat_boxes,
-dva_zbuffer_splat).  Compaction of the kept set / winner map is index plumbing (torch.nonzero).
+Kernels: csrc/zbuffer.cu through the C ABI (dva_project_equirectangular, dva_project_camera,
+dva_splat_boxes, dva_splat_boxes_from_width, dva_zbuffer_splat).  Compaction of the kept set / winner map is index plumbing (torch.nonzero).
 Depth-map and Biasutti visibility models are out of scope (not used by any shipped config).
 """
 import ctypes
@@ -37,35 +37,118 @@ def pose_to_rotation_matrix(opk):
     return torch.from_numpy(np.dot(m_o, np.dot(m_p, m_k)).astype(np.float32))
 
 
+def _camera_transform(camera, img_extrinsic):
+    """(A, t0, t1) float32 with p = A (xyz - t0) + t1 (visibility.py:231-244, 304-310)."""
+    E = np.ascontiguousarray(np.asarray(
+        img_extrinsic.detach().cpu().numpy() if isinstance(img_extrinsic, torch.Tensor) else img_extrinsic,
+        dtype=np.float32))
+    if camera == 'scannet':
+        c2w = np.linalg.inv(E)
+        return c2w[:3, :3].copy(), np.zeros(3, np.float32), c2w[:3, 3].copy()
+    return E[:3, :3].T.copy(), E[:3, 3].copy(), np.zeros(3, np.float32)
+
+
+def _host_f32(t, n):
+    t = t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+    return np.asarray(t, dtype=np.float32).reshape(-1)[:n]
+
+
 def camera_projection(xyz, img_xyz, img_opk=None, img_intrinsic_pinhole=None, img_intrinsic_fisheye=None,
                       img_extrinsic=None, img_mask=None, img_size=(1024, 512), crop_top=0, crop_bottom=0,
                       r_max=30, r_min=0.5, camera='s3dis_equirectangular', **kwargs):
     """-> (indices int64[m], dist f32[m], x_proj f64[m], y_proj f64[m]) of the points within
-    (r_min, r_max) of the camera that project inside the (cropped) image."""
+    (r_min, r_max) of the camera that project inside the (cropped) image and its mask
+    (visibility.py:478-538).  Cameras: s3dis_equirectangular, scannet, kitti360_perspective,
+    kitti360_fisheye."""
     require_cuda(xyz)
-    if camera != 's3dis_equirectangular':
-        raise NotImplementedError(
-            f"camera='{camera}': only the equirectangular projection has a CUDA kernel so far "
-            f"(pinhole / fisheye projections are listed as next in DESIGN.md)")
-    if img_mask is not None:
-        raise NotImplementedError("img_mask is not supported by the CUDA projection yet")
     lib = _lib.load()
     dev = xyz.device
     xyz = xyz.float().contiguous()
     n = xyz.shape[0]
-    rot = pose_to_rotation_matrix(img_opk if img_opk is not None else np.zeros(3, np.float32))
-    pose = torch.cat([torch.as_tensor(img_xyz, dtype=torch.float32).cpu().view(3), rot.view(9)]).to(dev)
+    W, H = int(img_size[0]), int(img_size[1])
     dist = torch.empty(n, dtype=torch.float32, device=dev)
     x_proj = torch.empty(n, dtype=torch.float64, device=dev)
     y_proj = torch.empty(n, dtype=torch.float64, device=dev)
     keep = torch.empty(n, dtype=torch.uint8, device=dev)
+    cam_xyz = _host_f32(img_xyz, 3)
     with torch.cuda.device(dev):
-        check(lib.dva_project_equirectangular(ptr(xyz), ptr(pose), ptr(dist), ptr(x_proj), ptr(y_proj), ptr(keep),
-                                              n, int(img_size[0]), int(img_size[1]), int(crop_top),
-                                              int(crop_bottom), float(r_min), float(r_max), stream_ptr()),
-              "dva_project_equirectangular")
+        if camera == 's3dis_equirectangular':
+            rot = pose_to_rotation_matrix(img_opk if img_opk is not None else np.zeros(3, np.float32))
+            pose = torch.from_numpy(np.concatenate([cam_xyz, rot.numpy().reshape(-1)])).to(dev)
+            check(lib.dva_project_equirectangular(ptr(xyz), ptr(pose), ptr(dist), ptr(x_proj), ptr(y_proj),
+                                                  ptr(keep), n, W, H, int(crop_top), int(crop_bottom),
+                                                  float(r_min), float(r_max), stream_ptr()),
+                  "dva_project_equirectangular")
+        elif camera in _PINHOLE_CAMERAS or camera == 'kitti360_fisheye':
+            A, t0, t1 = _camera_transform(camera, img_extrinsic)
+            intr = np.zeros(8, np.float32)
+            if camera == 'kitti360_fisheye':
+                intr[:7] = _host_f32(img_intrinsic_fisheye, 7)
+                code = 3
+            else:
+                K = img_intrinsic_pinhole.detach().cpu().numpy() if isinstance(img_intrinsic_pinhole, torch.Tensor) \
+                    else np.asarray(img_intrinsic_pinhole)
+                K = np.asarray(K, dtype=np.float32)
+                intr[:4] = [K[0, 0], K[1, 1], K[0, 2], K[1, 2]]
+                code = 1
+            cam = torch.from_numpy(np.concatenate([cam_xyz, A.reshape(-1), t0, t1, intr]).astype(np.float32)).to(dev)
+            check(lib.dva_project_camera(ptr(xyz), ptr(cam), code, ptr(dist), ptr(x_proj), ptr(y_proj), ptr(keep),
+                                         n, W, H, int(crop_top), int(crop_bottom), float(r_min), float(r_max),
+                                         stream_ptr()), "dva_project_camera")
+        else:
+            raise ValueError(f"unknown camera '{camera}'")
+    if img_mask is not None:  # field_of_view_cpu: img_mask[floor(x), floor(y)] (visibility.py:428-434)
+        assert tuple(img_mask.shape) == (W, H), \
+            f'Expected img_mask to be a torch.BoolTensor of shape img_size={img_size} but got size={img_mask.shape}.'
+        xi = x_proj.floor().long().clamp(0, W - 1)
+        yi = y_proj.floor().long().clamp(0, H - 1)
+        keep = keep.bool() & img_mask.to(dev)[xi, yi]
     indices = torch.nonzero(keep, as_tuple=False).view(-1)
     return indices, dist[indices], x_proj[indices], y_proj[indices]
+
+
+def _project_raw(xyz, camera, img_extrinsic, intr8, code):
+    """x_proj, y_proj of every row of xyz (no filtering) through dva_project_camera."""
+    lib = _lib.load()
+    dev, n = xyz.device, xyz.shape[0]
+    A, t0, t1 = _camera_transform(camera, img_extrinsic)
+    cam = torch.from_numpy(np.concatenate([np.zeros(3, np.float32), A.reshape(-1), t0, t1, intr8])
+                           .astype(np.float32)).to(dev)
+    d = torch.empty(n, dtype=torch.float32, device=dev)
+    xp = torch.empty(n, dtype=torch.float64, device=dev)
+    yp = torch.empty(n, dtype=torch.float64, device=dev)
+    keep = torch.empty(n, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.dva_project_camera(ptr(xyz), ptr(cam), code, ptr(d), ptr(xp), ptr(yp), ptr(keep), n, 1 << 20,
+                                     1 << 20, 0, 0, 0.0, 1e30, stream_ptr()), "dva_project_camera")
+    return xp, yp
+
+
+def fisheye_splat_boxes(x_proj, y_proj, xyz, img_extrinsic, img_intrinsic_fisheye, img_size=(1024, 512),
+                        crop_top=0, crop_bottom=0, voxel=0.02, k_swell=1.0, d_swell=1000,
+                        camera='kitti360_fisheye'):
+    """fisheye_splat_cpu (visibility.py:876-953): the splat width is twice the image distance between
+    a point and the projection of the top of its voxel (xyz + [0, 0, swell * voxel / 2]); NB the
+    reference takes `dist = norm(xyz)` of the ABSOLUTE coordinates here (:900), reproduced."""
+    require_cuda(x_proj, y_proj, xyz)
+    lib = _lib.load()
+    xyz = xyz.float().contiguous()
+    m = xyz.shape[0]
+    d = torch.sqrt((xyz ** 2).sum(dim=1))                                   # float32, like norm_cpu
+    swell = 1 + k_swell * torch.exp(-d.double() / np.log(d_swell))          # float64, like numba
+    top = xyz.clone()
+    top[:, 2] += (swell * voxel / 2).float()                                # z_offset is float32
+    intr = np.zeros(8, np.float32)
+    intr[:7] = _host_f32(img_intrinsic_fisheye, 7)
+    xt, yt = _project_raw(top, camera, img_extrinsic, intr, 3)
+    width = 2 * torch.sqrt((x_proj.double() - xt) ** 2 + (y_proj.double() - yt) ** 2)
+    splat = torch.empty((m, 4), dtype=torch.int32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        check(lib.dva_splat_boxes_from_width(ptr(x_proj.double().contiguous()), ptr(y_proj.double().contiguous()),
+                                             ptr(width.contiguous()), ptr(splat), m, int(img_size[0]),
+                                             int(img_size[1]), int(crop_top), int(crop_bottom), stream_ptr()),
+              "dva_splat_boxes_from_width")
+    return splat
 
 
 def splat_boxes(x_proj, y_proj, dist, img_intrinsic_pinhole=None, img_size=(1024, 512), crop_top=0,
@@ -107,8 +190,12 @@ def visibility_from_splatting(x_proj, y_proj, dist, xyz=None, img_extrinsic=None
     xp, yp = x_proj.double().contiguous(), y_proj.double().contiguous()
     d = dist.float().contiguous()
     m = d.shape[0]
-    splat = splat_boxes(xp, yp, d, img_intrinsic_pinhole, img_size, crop_top, crop_bottom, voxel, k_swell,
-                        d_swell, camera)
+    if camera == 'kitti360_fisheye':
+        splat = fisheye_splat_boxes(xp, yp, xyz, img_extrinsic, img_intrinsic_fisheye, img_size, crop_top,
+                                    crop_bottom, voxel, k_swell, d_swell, camera)
+    else:
+        splat = splat_boxes(xp, yp, d, img_intrinsic_pinhole, img_size, crop_top, crop_bottom, voxel, k_swell,
+                            d_swell, camera)
     zbuf = torch.empty(W * Hc, dtype=torch.int64, device=dev)       # uint64 keys
     idx_map = torch.empty((W, Hc), dtype=torch.int64, device=dev)
     seen = torch.empty(m, dtype=torch.uint8, device=dev) if exact else None

@@ -59,6 +59,56 @@ project_equirect_kernel(const float* __restrict__ xyz, const float* __restrict__
   }
 }
 
+// ---- Z1: pinhole / fisheye projection (visibility.py:219-339) --------------------------------
+// cam = [img_xyz(3), A(9), t0(3), t1(3), intr(8)] fp32 on device, p = A (xyz - t0) + t1:
+//   scannet               A = R(c2w), t0 = 0, t1 = T(c2w), c2w = inv(extrinsic)   (:233-236)
+//   kitti360_{persp,fish}  A = R^T,    t0 = T, t1 = 0                              (:239-242, :305-308)
+// camera 1: pinhole, intr = fx, fy, cx, cy (float32 arithmetic like numba, then float64)
+// camera 3: fisheye, intr = xi, k1, k2, gamma1, gamma2, u0, v0 (float64 after the norm, like numba)
+__global__ void __launch_bounds__(256)
+project_camera_kernel(const float* __restrict__ xyz, const float* __restrict__ cam, int camera,
+                      float* __restrict__ dist, double* __restrict__ x_proj,
+                      double* __restrict__ y_proj, uint8_t* __restrict__ keep, int64_t n, int W, int H,
+                      int crop_top, int crop_bottom, float r_min, float r_max) {
+  float c[26];
+#pragma unroll
+  for (int j = 0; j < 26; ++j) c[j] = cam[j];
+  const float* A = c + 3; const float* t0 = c + 12; const float* t1 = c + 15; const float* in = c + 18;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
+    const float dx = px - c[0], dy = py - c[1], dz = pz - c[2];
+    const float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    dist[i] = d;
+    const float q0 = px - t0[0], q1 = py - t0[1], q2 = pz - t0[2];
+    const float p0 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(A[0], q0), __fmul_rn(A[1], q1)), __fmul_rn(A[2], q2)), t1[0]);
+    const float p1 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(A[3], q0), __fmul_rn(A[4], q1)), __fmul_rn(A[5], q2)), t1[1]);
+    const float p2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(A[6], q0), __fmul_rn(A[7], q1)), __fmul_rn(A[8], q2)), t1[2]);
+    double x, y, z;
+    if (camera == 1) {
+      x = (double)__fadd_rn(__fdiv_rn(__fmul_rn(p0, in[0]), p2), in[2]);
+      y = (double)__fadd_rn(__fdiv_rn(__fmul_rn(p1, in[1]), p2), in[3]);
+      z = (double)p2;
+    } else {
+      const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(p0, p0), __fmul_rn(p1, p1)), __fmul_rn(p2, p2)));
+      const double den = (double)nrm + 1e-4;
+      double fx = (double)p0 / den, fy = (double)p1 / den;
+      const double fz = (double)p2 / den;
+      fx /= fz + (double)in[0];
+      fy /= fz + (double)in[0];
+      const double r2 = fx * fx + fy * fy, r4 = r2 * r2;
+      x = (double)in[3] * (1.0 + (double)in[1] * r2 + (double)in[2] * r4) * fx + (double)in[5];
+      y = (double)in[4] * (1.0 + (double)in[1] * r2 + (double)in[2] * r4) * fy + (double)in[6];
+      z = (double)__fmul_rn(nrm, p2) / fabs((double)p2 + 1e-4);
+    }
+    x_proj[i] = x; y_proj[i] = y;
+    const bool in_range = (r_min < d) && (d < r_max);
+    const bool in_fov = (0.0 <= x) && (x < (double)W) && ((double)crop_top <= y) &&
+                        (y < (double)(H - crop_bottom)) && (0.0 < z);
+    keep[i] = (in_range && in_fov) ? 1 : 0;
+  }
+}
+
 // ---- Z2: splat boxes ------------------------------------------------------------------------
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
@@ -95,6 +145,25 @@ splat_boxes_kernel(const double* __restrict__ x_proj, const double* __restrict__
     ya = clampi(ya, y_min, y_max - 1);
     yb = clampi(yb, y_min + 1, y_max);
     reinterpret_cast<int4*>(splat)[i] = make_int4(xa, xb, ya, yb);
+  }
+}
+
+// fisheye: the splat width comes from a second projection of the voxel top (visibility.py:903-914),
+// computed by the host mirror; this kernel only rounds and clamps like the other cameras.
+__global__ void __launch_bounds__(256)
+splat_boxes_width_kernel(const double* __restrict__ x_proj, const double* __restrict__ y_proj,
+                         const double* __restrict__ width, int32_t* __restrict__ splat, int64_t m,
+                         int W, int H, int crop_top, int crop_bottom) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const double xp = x_proj[i], yp = y_proj[i], w = width[i];
+    int xa = (int)(float)rint(xp - w / 2.0);
+    int xb = (int)(float)rint(xp + w / 2.0 + 1.0);
+    int ya = (int)(float)rint(yp - w / 2.0);
+    int yb = (int)(float)rint(yp + w / 2.0 + 1.0);
+    const int y_min = crop_top, y_max = H - crop_bottom;
+    reinterpret_cast<int4*>(splat)[i] = make_int4(clampi(xa, 0, W - 1), clampi(xb, 1, W),
+                                                  clampi(ya, y_min, y_max - 1), clampi(yb, y_min + 1, y_max));
   }
 }
 
@@ -180,6 +249,20 @@ extern "C" int dva_project_equirectangular(const float* xyz, const float* img_po
   return check_launch("project_equirect");
 }
 
+extern "C" int dva_project_camera(const float* xyz, const float* cam, int camera, float* dist,
+                                  double* x_proj, double* y_proj, uint8_t* keep, int64_t n, int64_t W,
+                                  int64_t H, int64_t crop_top, int64_t crop_bottom, float r_min,
+                                  float r_max, void* stream) {
+  if (n < 0 || W < 1 || H < 1 || crop_top < 0 || crop_bottom < 0 || crop_top + crop_bottom >= H)
+    return fail(DVA_EINVAL, "project_camera: bad sizes");
+  if (camera != 1 && camera != 3) return fail(DVA_EUNSUPPORTED, "project_camera: camera must be 1 (pinhole) or 3 (fisheye)");
+  if (n == 0) return DVA_OK;
+  if (!xyz || !cam || !dist || !x_proj || !y_proj || !keep) return fail(DVA_EINVAL, "project_camera: null pointer");
+  project_camera_kernel<<<z_grid(n), 256, 0, (cudaStream_t)stream>>>(
+      xyz, cam, camera, dist, x_proj, y_proj, keep, n, (int)W, (int)H, (int)crop_top, (int)crop_bottom, r_min, r_max);
+  return check_launch("project_camera");
+}
+
 extern "C" int dva_splat_boxes(const double* x_proj, const double* y_proj, const float* dist,
                                int32_t* splat, int64_t m, int64_t W, int64_t H, int64_t crop_top,
                                int64_t crop_bottom, double voxel, double k_swell, double d_swell,
@@ -194,6 +277,19 @@ extern "C" int dva_splat_boxes(const double* x_proj, const double* y_proj, const
       x_proj, y_proj, dist, splat, m, (int)W, (int)H, (int)crop_top, (int)crop_bottom, voxel,
       k_swell, log(d_swell), camera, fx, fy);
   return check_launch("splat_boxes");
+}
+
+extern "C" int dva_splat_boxes_from_width(const double* x_proj, const double* y_proj,
+                                          const double* width, int32_t* splat, int64_t m, int64_t W,
+                                          int64_t H, int64_t crop_top, int64_t crop_bottom, void* stream) {
+  if (m < 0 || W < 1 || H < 1 || crop_top < 0 || crop_bottom < 0 || crop_top + crop_bottom >= H)
+    return fail(DVA_EINVAL, "splat_boxes_from_width: bad sizes");
+  if (m == 0) return DVA_OK;
+  if (!x_proj || !y_proj || !width || !splat) return fail(DVA_EINVAL, "splat_boxes_from_width: null pointer");
+  if (!aligned16(splat)) return fail(DVA_EALIGN, "splat_boxes_from_width: splat must be 16-byte aligned");
+  splat_boxes_width_kernel<<<z_grid(m), 256, 0, (cudaStream_t)stream>>>(
+      x_proj, y_proj, width, splat, m, (int)W, (int)H, (int)crop_top, (int)crop_bottom);
+  return check_launch("splat_boxes_from_width");
 }
 
 extern "C" int dva_zbuffer_splat(const int32_t* splat, const float* dist, const double* x_proj,

@@ -178,6 +178,13 @@ int dva_splat_boxes(const double* x_proj, const double* y_proj, const float* dis
                     int64_t crop_bottom, double voxel, double k_swell, double d_swell, int camera,
                     double fx, double fy, void* stream);
 
+/* Z2  splat boxes from explicit widths        replaces the rounding / clamping tail of
+ *   fisheye_splat_cpu (visibility.py:916-951); width [m] fp64 = 2*|proj(xyz) - proj(xyz + dz)|
+ *   (visibility.py:903-914) is produced by the host mirror with two dva_project_camera calls. */
+int dva_splat_boxes_from_width(const double* x_proj, const double* y_proj, const double* width,
+                               int32_t* splat, int64_t m, int64_t W, int64_t H, int64_t crop_top,
+                               int64_t crop_bottom, void* stream);
+
 /* Z1  equirectangular camera projection      replaces visibility.py:150-182 + :509-513 + :395-435
  *   xyz [n,3] fp32; img_pose [12] fp32 on device = camera position (3) followed by the 3x3
  *   rotation matrix of pose_to_rotation_matrix (visibility.py:57-90), row-major, computed by the
@@ -187,6 +194,16 @@ int dva_project_equirectangular(const float* xyz, const float* img_pose, float* 
                                 double* x_proj, double* y_proj, uint8_t* keep, int64_t n,
                                 int64_t W, int64_t H, int64_t crop_top, int64_t crop_bottom,
                                 float r_min, float r_max, void* stream);
+
+/* Z1  pinhole / fisheye camera projection    replaces visibility.py:219-252 (pinhole_projection_cpu,
+ *   cameras 'scannet' and 'kitti360_perspective'), :288-339 (fisheye_projection_cpu,
+ *   'kitti360_fisheye') + the range / field-of-view filter of camera_projection_cpu :509-536.
+ *   cam [26] fp32 on device = img_xyz(3), A(9 row-major), t0(3), t1(3), intr(8) with
+ *   p = A (xyz - t0) + t1  (scannet: A,t1 from inv(extrinsic), t0 = 0; kitti360: A = R^T, t0 = T);
+ *   camera 1 = pinhole (intr = fx, fy, cx, cy), 3 = fisheye (intr = xi,k1,k2,gamma1,gamma2,u0,v0). */
+int dva_project_camera(const float* xyz, const float* cam, int camera, float* dist, double* x_proj,
+                       double* y_proj, uint8_t* keep, int64_t n, int64_t W, int64_t H,
+                       int64_t crop_top, int64_t crop_bottom, float r_min, float r_max, void* stream);
 
 /* C1  CSR pointers from sorted dense ids     replaces csr.py:158-172 + :197-229
  *   ids [n] int64 sorted ascending, values in [0,num_groups) -> ptr [num_groups+1] int64 with

@@ -190,6 +190,62 @@ def main():
 
     make_integer_golden(ref)
     make_branch_golden(ref)
+    make_camera_golden(ref)
+
+
+def make_camera_golden(ref):
+    """numba camera_projection_cpu for the pinhole (scannet, kitti360_perspective) and fisheye
+    (kitti360_fisheye) cameras (visibility.py:219-339, 478-538)."""
+    import numpy as np
+    vis = ref.visibility
+    gen = torch.Generator().manual_seed(17)
+    n = 6000
+    xyz = (torch.rand(n, 3, generator=gen) - 0.5) * torch.tensor([10., 10., 4.])
+
+    def rot(ax, ay, az):
+        cx, sx, cy, sy, cz, sz = np.cos(ax), np.sin(ax), np.cos(ay), np.sin(ay), np.cos(az), np.sin(az)
+        rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+        ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+        rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+        return rz @ ry @ rx
+    cam_pos = np.array([0.4, -0.3, 0.2])
+    c2w = np.eye(4)
+    c2w[:3, :3] = rot(-1.4, 0.1, 0.5)
+    c2w[:3, 3] = cam_pos
+    intr = np.eye(4, dtype=np.float32)
+    intr[0, 0], intr[1, 1], intr[0, 2], intr[1, 2] = 250.0, 250.0, 159.5, 119.5
+    fish = np.array([2.2134, 0.016798, 0.7572, 1336.3, 1335.7, 716.94, 705.76], dtype=np.float32)
+    cases = {
+        # scannet: img_extrinsic is world->camera (inverted inside), kitti360: camera->world
+        "scannet": dict(ext=torch.from_numpy(np.linalg.inv(c2w)).float(), size=(320, 240), crop=(0, 0),
+                        pin=torch.from_numpy(intr), fish=None),
+        "kitti360_perspective": dict(ext=torch.from_numpy(c2w).float(), size=(320, 240), crop=(10, 20),
+                                     pin=torch.from_numpy(intr), fish=None),
+        "kitti360_fisheye": dict(ext=torch.from_numpy(c2w).float(), size=(1400, 1400), crop=(0, 0), pin=None,
+                                 fish=torch.from_numpy(fish)),
+    }
+    for cam, c in cases.items():
+        idx, dist, xp, yp = vis.camera_projection_cpu(
+            xyz, torch.from_numpy(cam_pos).float(), img_intrinsic_pinhole=c["pin"],
+            img_intrinsic_fisheye=c["fish"], img_extrinsic=c["ext"], img_size=c["size"], crop_top=c["crop"][0],
+            crop_bottom=c["crop"][1], r_max=8, r_min=0.3, camera=cam)
+        extra = {}
+        if cam == "kitti360_fisheye":   # fisheye splat + z-buffer (visibility.py:876-953, 1126-1130)
+            sp = vis.fisheye_splat_cpu(xp.numpy(), yp.numpy(), xyz[idx].numpy(), c["ext"].numpy(), c["fish"].numpy(),
+                                       img_size=c["size"], crop_top=0, crop_bottom=0, voxel=0.05, k_swell=1.0,
+                                       d_swell=1000)
+            extra["splat"] = sp
+            for exact in (False, True):
+                i2, xpix, ypix = vis.visibility_from_splatting_cpu(
+                    xp, yp, dist, xyz[idx], img_extrinsic=c["ext"], img_intrinsic_fisheye=c["fish"],
+                    img_size=c["size"], voxel=0.05, k_swell=1.0, d_swell=1000, exact=exact, camera=cam)
+                extra[f"vis_idx_{int(exact)}"], extra[f"vis_x_{int(exact)}"], extra[f"vis_y_{int(exact)}"] = i2, xpix, ypix
+        if cam == "scannet":
+            extra["c2w"] = np.linalg.inv(np.ascontiguousarray(c["ext"].numpy()))  # numba's own inverse (f32)
+        save(f"camera_{cam}", xyz=xyz, img_xyz=torch.from_numpy(cam_pos).float(), ext=c["ext"],
+             pin=c["pin"] if c["pin"] is not None else np.zeros(0), fish=c["fish"] if c["fish"] is not None else np.zeros(0),
+             size=np.array(c["size"]), crop=np.array(c["crop"]), r=np.array([0.3, 8.0]),
+             proj_idx=idx, dist=dist, x_proj=xp, y_proj=yp, **extra)
 
 
 def toy_settings(gen, n_points, specs, F=8):

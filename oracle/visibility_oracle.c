@@ -47,6 +47,46 @@ void oracle_project_equirect(const float* xyz, const float* img_xyz, const float
   }
 }
 
+/* Pinhole (camera 1) and fisheye (camera 3) projections, visibility.py:219-339.  The rigid
+ * transform is passed as p = A . (xyz - t0) + t1:  scannet  A = R(c2w), t0 = 0, t1 = T(c2w) with
+ * c2w = inv(extrinsic) (:233-236);  kitti360  A = R^T, t0 = T, t1 = 0 (:239-242, :305-308).
+ * intr = fx, fy, cx, cy  |  xi, k1, k2, gamma1, gamma2, u0, v0. */
+void oracle_project_camera(const float* xyz, const float* img_xyz, const float* A, const float* t0,
+                           const float* t1, const float* intr, int camera, int64_t n, int W, int H,
+                           int crop_top, int crop_bottom, float r_min, float r_max, float* dist,
+                           double* x_proj, double* y_proj, uint8_t* keep) {
+  for (int64_t i = 0; i < n; ++i) {
+    const float dx = xyz[3 * i] - img_xyz[0], dy = xyz[3 * i + 1] - img_xyz[1], dz = xyz[3 * i + 2] - img_xyz[2];
+    const float d = sqrtf((dx * dx + dy * dy) + dz * dz);
+    dist[i] = d;
+    const float q0 = xyz[3 * i] - t0[0], q1 = xyz[3 * i + 1] - t0[1], q2 = xyz[3 * i + 2] - t0[2];
+    const float p0 = ((A[0] * q0 + A[1] * q1) + A[2] * q2) + t1[0];
+    const float p1 = ((A[3] * q0 + A[4] * q1) + A[5] * q2) + t1[1];
+    const float p2 = ((A[6] * q0 + A[7] * q1) + A[8] * q2) + t1[2];
+    double x, y, z;
+    if (camera == 1) {
+      x = (double)(p0 * intr[0] / p2 + intr[2]);      /* float32 arithmetic, then astype(float64) */
+      y = (double)(p1 * intr[1] / p2 + intr[3]);
+      z = (double)p2;
+    } else {
+      const float nrm = sqrtf((p0 * p0 + p1 * p1) + p2 * p2);
+      const double den = (double)nrm + 1e-4;
+      double fx = (double)p0 / den, fy = (double)p1 / den;
+      const double fz = (double)p2 / den;
+      fx /= fz + (double)intr[0];
+      fy /= fz + (double)intr[0];
+      const double r2 = fx * fx + fy * fy, r4 = r2 * r2;
+      x = (double)intr[3] * (1.0 + (double)intr[1] * r2 + (double)intr[2] * r4) * fx + (double)intr[5];
+      y = (double)intr[4] * (1.0 + (double)intr[1] * r2 + (double)intr[2] * r4) * fy + (double)intr[6];
+      z = (double)(nrm * p2) / fabs((double)p2 + 1e-4);
+    }
+    x_proj[i] = x; y_proj[i] = y;
+    const int in_range = (r_min < d) && (d < r_max);
+    const int in_fov = (0.0 <= x) && (x < (double)W) && ((double)crop_top <= y) && (y < (double)(H - crop_bottom)) && (0.0 < z);
+    keep[i] = (uint8_t)(in_range && in_fov);
+  }
+}
+
 static void finish_box(double xp, double yp, double wx, double wy, int W, int H, int crop_top,
                        int crop_bottom, int32_t* out) {
   /* np.round(value, 0, out=float32 array) then astype(int32): round half to even */

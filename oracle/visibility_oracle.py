@@ -58,6 +58,61 @@ def project_equirect(xyz, img_xyz, rotation, W, H, crop_top=0, crop_bottom=0, r_
     return dist, xp, yp, keep.astype(bool)
 
 
+def camera_transform(camera, img_extrinsic):
+    """(A, t0, t1) with p = A (xyz - t0) + t1, float32 (visibility.py:231-244, 304-310)."""
+    E = np.ascontiguousarray(np.asarray(img_extrinsic, dtype=np.float32))
+    if camera == "scannet":
+        c2w = np.linalg.inv(E)
+        return c2w[:3, :3].copy(), np.zeros(3, np.float32), c2w[:3, 3].copy()
+    return E[:3, :3].T.copy(), E[:3, 3].copy(), np.zeros(3, np.float32)
+
+
+def project_camera(xyz, img_xyz, camera, img_extrinsic, intrinsic, W, H, crop_top=0, crop_bottom=0,
+                   r_min=0.5, r_max=30.0):
+    """Pinhole ('scannet', 'kitti360_perspective': intrinsic = 4x4 matrix) or fisheye
+    ('kitti360_fisheye': intrinsic = [xi,k1,k2,gamma1,gamma2,u0,v0]) projection."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    n = xyz.shape[0]
+    A, t0, t1 = [np.ascontiguousarray(v, dtype=np.float32) for v in camera_transform(camera, img_extrinsic)]
+    intr = np.zeros(8, np.float32)
+    if camera == "kitti360_fisheye":
+        intr[:7] = np.asarray(intrinsic, dtype=np.float32)
+        cam = 3
+    else:
+        K = np.asarray(intrinsic, dtype=np.float32)
+        intr[:4] = [K[0, 0], K[1, 1], K[0, 2], K[1, 2]]
+        cam = 1
+    dist = np.empty(n, np.float32)
+    xp, yp = np.empty(n, np.float64), np.empty(n, np.float64)
+    keep = np.empty(n, np.uint8)
+    c = np.ascontiguousarray(img_xyz, dtype=np.float32)
+    _load().oracle_project_camera(_p(xyz), _p(c), _p(A.reshape(-1)), _p(t0), _p(t1), _p(intr), cam,
+                                  ctypes.c_int64(n), W, H, crop_top, crop_bottom, ctypes.c_float(r_min),
+                                  ctypes.c_float(r_max), _p(dist), _p(xp), _p(yp), _p(keep))
+    return dist, xp, yp, keep.astype(bool)
+
+
+def fisheye_splat(x_proj, y_proj, xyz, img_extrinsic, fish, W, H, crop_top=0, crop_bottom=0, voxel=0.02,
+                  k_swell=1.0, d_swell=1000.0):
+    """fisheye_splat_cpu, visibility.py:876-953 (width from the projection of the voxel top;
+    `dist = norm_cpu(xyz)` of the absolute coordinates, :900)."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    d = np.sqrt((xyz ** 2).sum(axis=1)).astype(np.float32)
+    swell = 1 + k_swell * np.exp(-d.astype(np.float64) / np.log(d_swell))
+    top = xyz.copy()
+    top[:, 2] += (swell * voxel / 2).astype(np.float32)
+    _, xt, yt, _ = project_camera(top, np.zeros(3, np.float32), "kitti360_fisheye", img_extrinsic, fish,
+                                  1 << 20, 1 << 20, 0, 0, 0.0, 1e30)
+    w = 2 * np.sqrt((np.asarray(x_proj, np.float64) - xt) ** 2 + (np.asarray(y_proj, np.float64) - yt) ** 2)
+    xa = np.rint(x_proj - w / 2).astype(np.float32).astype(np.int32)
+    xb = np.rint(x_proj + w / 2 + 1).astype(np.float32).astype(np.int32)
+    ya = np.rint(y_proj - w / 2).astype(np.float32).astype(np.int32)
+    yb = np.rint(y_proj + w / 2 + 1).astype(np.float32).astype(np.int32)
+    y_min, y_max = crop_top, H - crop_bottom
+    return np.stack([np.clip(xa, 0, W - 1), np.clip(xb, 1, W), np.clip(ya, y_min, y_max - 1),
+                     np.clip(yb, y_min + 1, y_max)], axis=1).astype(np.int32)
+
+
 def splat_boxes(x_proj, y_proj, dist, W, H, crop_top=0, crop_bottom=0, voxel=0.02, k_swell=1.0,
                 d_swell=1000.0, camera="equirectangular", fx=0.0, fy=0.0):
     xp = np.ascontiguousarray(x_proj, np.float64)

@@ -103,3 +103,71 @@ def test_csr_kernels_vs_oracle():
                                          sel.numel(), val.numel(), _lib.stream_ptr()), "select")
     assert np.array_equal(_np(val), val_ref)
     assert torch.equal(g["images"][val.cpu()], g["sel_images"])
+
+
+@pytest.mark.parametrize("cam", ["scannet", "kitti360_perspective", "kitti360_fisheye"])
+def test_pinhole_fisheye_cameras_vs_numba_fixture(cam):
+    from deepviewagg_b200.core.multimodal import visibility as V
+    g = load_golden("camera_" + cam)
+    W, H = [int(v) for v in g["size"]]
+    ct, cb = [int(v) for v in g["crop"]]
+    fish = cam == "kitti360_fisheye"
+    idx, dist, xp, yp = V.camera_projection(
+        g["xyz"].cuda(), g["img_xyz"], img_intrinsic_pinhole=None if fish else g["pin"],
+        img_intrinsic_fisheye=g["fish"] if fish else None, img_extrinsic=g["ext"], img_size=(W, H), crop_top=ct,
+        crop_bottom=cb, r_max=float(g["r"][1]), r_min=float(g["r"][0]), camera=cam)
+    assert torch.equal(idx.cpu(), g["proj_idx"]) and torch.equal(dist.cpu(), g["dist"])
+    assert torch.equal(xp.cpu().floor(), g["x_proj"].floor()) and torch.equal(yp.cpu().floor(), g["y_proj"].floor())
+    assert (xp.cpu() - g["x_proj"]).abs().max() < 2e-4
+    # image mask: drop the left half
+    mask = torch.ones(W, H, dtype=torch.bool)
+    mask[: W // 2] = False
+    idx_m, _, xm, _ = V.camera_projection(
+        g["xyz"].cuda(), g["img_xyz"], img_intrinsic_pinhole=None if fish else g["pin"],
+        img_intrinsic_fisheye=g["fish"] if fish else None, img_extrinsic=g["ext"], img_mask=mask, img_size=(W, H),
+        crop_top=ct, crop_bottom=cb, r_max=float(g["r"][1]), r_min=float(g["r"][0]), camera=cam)
+    assert torch.equal(idx_m.cpu(), g["proj_idx"][g["x_proj"] >= W // 2]) and (xm >= W // 2).all()
+    if fish:
+        xr, yr, dr = g["x_proj"].cuda(), g["y_proj"].cuda(), g["dist"].cuda()
+        xyz_kept = g["xyz"][g["proj_idx"]].cuda()
+        sp = V.fisheye_splat_boxes(xr, yr, xyz_kept, g["ext"], g["fish"], (W, H), voxel=0.05)
+        assert (sp.cpu() == g["splat"].int()).all(dim=1).double().mean() > 0.995
+        i2, x2, y2 = V.visibility_from_splatting(xr, yr, dr, xyz_kept, img_extrinsic=g["ext"],
+                                                 img_intrinsic_fisheye=g["fish"], img_size=(W, H), voxel=0.05,
+                                                 exact=True, camera=cam)
+        # exact mode only depends on WHICH points are seen: robust to the rare 1-px box differences
+        ref = set(g["vis_idx_1"].tolist())
+        got = set(i2.cpu().tolist())
+        assert len(ref ^ got) <= max(2, len(ref) // 200)
+
+
+def test_map_images_equals_per_image_oracle():
+    """MapImages (image.py transform :162-428) == per-image C-oracle visibility + numpy from_dense."""
+    from deepviewagg_b200.core.multimodal.image import SameSettingImageData
+    from deepviewagg_b200.core.multimodal.mapping import MapImages
+    g = load_golden("zbuffer_nocrop")
+    W, H = [int(v) for v in g["size"]]
+    xyz = g["xyz"]
+    cams = torch.stack([g["img_xyz"], g["img_xyz"] + torch.tensor([1.5, -0.7, 0.1]), torch.tensor([50., 50., 50.])])
+    opk = torch.stack([g["img_opk"], g["img_opk"] * 0.5, g["img_opk"]])
+    images = SameSettingImageData(pos=cams, opk=opk, ref_size=(W // 2, H // 2), proj_upscale=2, downscale=1)
+    out = MapImages(voxel=0.05, exact=True, r_max=8, r_min=0.5)(xyz, images)
+    assert out.num_views == 2                                  # the far-away third camera sees nothing
+    m = out.mappings
+    assert m.num_groups == xyz.shape[0] and m.pixels.dtype == torch.int16 and m.features.shape[1] == 2
+    # oracle: same pipeline on the CPU
+    pid, iid, pix = [], [], []
+    for i in range(2):
+        R = VO.pose_to_rotation_matrix(_np(opk[i]))
+        dist, xp, yp, keep = VO.project_equirect(_np(xyz), _np(cams[i]), R, W, H, 0, 0, 0.5, 8.0)
+        idx = np.where(keep)[0]
+        sp = VO.splat_boxes(xp[idx], yp[idx], dist[idx], W, H, voxel=0.05)
+        i2, x2, y2, _ = VO.zbuffer(sp, dist[idx], xp[idx], yp[idx], W, H, exact=True)
+        p, x, y = idx[i2], x2 // 2, y2 // 2
+        u = VO.lexargunique(p, x, y)
+        pid.append(p[u]); iid.append(np.full(len(u), i)); pix.append(np.stack([x[u], y[u]], 1))
+    ref = VO.image_mapping_from_dense(np.concatenate(pid), np.concatenate(iid), np.concatenate(pix), None,
+                                      xyz.shape[0])
+    assert np.array_equal(_np(m.pointers), ref["pointers"]) and np.array_equal(_np(m.images), ref["images"])
+    assert np.array_equal(_np(m.atomic_csr_indexing), ref["atomic_pointers"])
+    assert np.array_equal(_np(m.pixels).astype(np.int64), ref["pixels"])

@@ -85,3 +85,28 @@ def test_pinhole_splat_vs_numba():
     sp = VO.splat_boxes(_np(g["x_proj"]), _np(g["y_proj"]), _np(g["dist"]), W, H, voxel=0.03, k_swell=1.0,
                         d_swell=1000, camera="pinhole", fx=float(g["fx"]), fy=float(g["fy"]))
     assert np.array_equal(sp, _np(g["splat"]))
+
+
+@pytest.mark.parametrize("cam", ["scannet", "kitti360_perspective", "kitti360_fisheye"])
+def test_pinhole_fisheye_projection_vs_numba(cam):
+    g = load_golden("camera_" + cam)
+    W, H = [int(v) for v in g["size"]]
+    ct, cb = [int(v) for v in g["crop"]]
+    intr = _np(g["fish"]) if cam == "kitti360_fisheye" else _np(g["pin"])
+    d, xp, yp, keep = VO.project_camera(_np(g["xyz"]), _np(g["img_xyz"]), cam, _np(g["ext"]), intr, W, H, ct, cb,
+                                        float(g["r"][0]), float(g["r"][1]))
+    idx = np.where(keep)[0]
+    assert np.array_equal(idx, _np(g["proj_idx"]))                    # same kept set
+    assert np.array_equal(d[idx], _np(g["dist"]))                     # float32 distances bit-exact
+    assert np.array_equal(np.floor(xp[idx]), np.floor(_np(g["x_proj"])))
+    assert np.array_equal(np.floor(yp[idx]), np.floor(_np(g["y_proj"])))
+    assert np.abs(xp[idx] - _np(g["x_proj"])).max() < 2e-4            # sub-pixel: sgemm rounding only
+    if cam == "kitti360_fisheye":
+        xr, yr, dr = _np(g["x_proj"]), _np(g["y_proj"]), _np(g["dist"])
+        sp = VO.fisheye_splat(xr, yr, _np(g["xyz"])[idx], _np(g["ext"]), intr, W, H, voxel=0.05)
+        ref = _np(g["splat"])
+        assert (sp == ref).all(axis=1).mean() > 0.995                  # width from a float32 projection
+        for exact in (0, 1):                                          # z-buffer on the reference's own boxes
+            i2, x2, y2, _ = VO.zbuffer(ref, dr, xr, yr, W, H, exact=bool(exact))
+            assert np.array_equal(i2, _np(g[f"vis_idx_{exact}"]))
+            assert np.array_equal(x2, _np(g[f"vis_x_{exact}"])) and np.array_equal(y2, _np(g[f"vis_y_{exact}"]))
