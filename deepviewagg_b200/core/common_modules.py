@@ -31,11 +31,27 @@ class FastBatchNorm1d(nn.Module):
         raise ValueError("Non supported number of dimensions {}".format(x.dim()))
 
 
+class MLPLayer(nn.Sequential):
+    """One `Linear -> FastBatchNorm1d -> activation` layer.  An nn.Sequential (children '0', '1',
+    '2': reference parameter names), whose forward fuses BatchNorm + LeakyReLU into two streaming
+    passes (ops.batch_norm_act) when the input is a CUDA [rows, C] matrix."""
+
+    def forward(self, x):
+        lin, bn, act = self[0], self[1], self[2]
+        fusable = (x.dim() == 2 and x.is_cuda and isinstance(bn, FastBatchNorm1d)
+                   and isinstance(act, (nn.LeakyReLU, nn.ReLU, nn.Identity, Identity)) and x.shape[0] > 0)
+        if not fusable:
+            return super().forward(x)
+        slope = act.negative_slope if isinstance(act, nn.LeakyReLU) else (0.0 if isinstance(act, nn.ReLU) else 1.0)
+        from .. import ops
+        return ops.batch_norm_act(lin(x), bn.batch_norm, negative_slope=slope)
+
+
 def MLP(channels, activation=None, bn_momentum=0.1, bias=True):
     """[Linear -> FastBatchNorm1d -> LeakyReLU(0.2)] per layer (base_modules.py:38-48)."""
     layers = []
     for i in range(1, len(channels)):
         act = activation if activation is not None else nn.LeakyReLU(0.2, inplace=True)
-        layers.append(nn.Sequential(nn.Linear(channels[i - 1], channels[i], bias=bias),
-                                    FastBatchNorm1d(channels[i], momentum=bn_momentum), act))
+        layers.append(MLPLayer(nn.Linear(channels[i - 1], channels[i], bias=bias),
+                               FastBatchNorm1d(channels[i], momentum=bn_momentum), act))
     return nn.Sequential(*layers)

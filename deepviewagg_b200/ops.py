@@ -434,3 +434,74 @@ class _GatherPool(torch.autograd.Function):
 def gather_pool(fmap, images, pixels, atomic_ptr, reduce="max", channels_last=False):
     """segment_csr(fmap[(images_per_pixel, :, py, px)], atomic_ptr, reduce) without the [P,C] copy."""
     return _GatherPool.apply(fmap, images, pixels, atomic_ptr, reduce, channels_last)
+
+
+# --------------------------------------------------------------------------------------------
+# fused BatchNorm1d + LeakyReLU over [rows, C] (base_modules.py:38-48, 131-156)
+# --------------------------------------------------------------------------------------------
+class _BNAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, weight, bias, running_mean, running_var, training, momentum, eps, slope):
+        require_cuda(z, weight, bias, running_mean, running_var)
+        lib = _lib.load()
+        z = z.contiguous()
+        R, C = z.shape
+        dev = z.device
+        gamma = weight.detach().float().contiguous() if weight is not None else None
+        beta = bias.detach().float().contiguous() if bias is not None else None
+        y = torch.empty_like(z)
+        if training:
+            mean = torch.empty(C, dtype=torch.float32, device=dev)
+            invstd = torch.empty(C, dtype=torch.float32, device=dev)
+        else:
+            mean = running_mean.float().contiguous()
+            invstd = torch.rsqrt(running_var.float() + eps).contiguous()
+        ws_bytes = int(lib.dva_bn_workspace_bytes(R, C))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        rm = running_mean if (training and running_mean is not None) else None
+        rv = running_var if (training and running_var is not None) else None
+        if not training:
+            rm, rv = running_mean, running_var
+        with torch.cuda.device(dev):
+            check(lib.dva_bn_act_fwd(ptr(z), ptr(gamma), ptr(beta), ptr(rm), ptr(rv), ptr(mean), ptr(invstd), ptr(y),
+                                     R, C, float(eps), float(momentum), float(slope), int(bool(training)),
+                                     dtype_code(z), ptr(ws), ws_bytes, stream_ptr()), "dva_bn_act_fwd")
+        ctx.cfg = (R, C, float(slope), bool(training), weight is not None, bias is not None,
+                   weight.dtype if weight is not None else None)
+        ctx.save_for_backward(z, gamma, beta, mean, invstd)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        z, gamma, beta, mean, invstd = ctx.saved_tensors
+        R, C, slope, training, has_w, has_b, wdt = ctx.cfg
+        lib = _lib.load()
+        dy = dy.contiguous()
+        dz = torch.empty_like(z)
+        sums = torch.empty((2, C), dtype=torch.float32, device=z.device)
+        ws_bytes = int(lib.dva_bn_workspace_bytes(R, C))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
+        with torch.cuda.device(z.device):
+            check(lib.dva_bn_act_bwd(ptr(dy), ptr(z), ptr(gamma), ptr(beta), ptr(mean), ptr(invstd), ptr(dz),
+                                     ptr(sums), R, C, slope, int(training), dtype_code(z), ptr(ws), ws_bytes,
+                                     stream_ptr()), "dva_bn_act_bwd")
+        gw = sums[1].to(wdt) if has_w else None
+        gb = sums[0].to(wdt) if has_b else None
+        return dz, gw, gb, None, None, None, None, None, None
+
+
+def batch_norm_act(z, bn, negative_slope=1.0):
+    """act(BatchNorm1d(z)) for z [rows, C] with the statistics / running-average semantics of
+    nn.BatchNorm1d (training: batch statistics over all rows, momentum update of the running
+    buffers, num_batches_tracked += 1).  `bn` is the nn.BatchNorm1d holding the parameters;
+    negative_slope = 1 gives plain BatchNorm, 0.2 the MLP layers of the pools."""
+    training = bn.training or (bn.running_mean is None and bn.running_var is None)
+    momentum = 0.0 if bn.momentum is None else bn.momentum
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        if bn.momentum is None:
+            momentum = 1.0 / float(bn.num_batches_tracked)
+    rm = bn.running_mean if bn.track_running_stats else None
+    rv = bn.running_var if bn.track_running_stats else None
+    return _BNAct.apply(z, bn.weight, bn.bias, rm, rv, training, momentum, bn.eps, negative_slope)

@@ -152,6 +152,27 @@ int dva_gather_pool_bwd(const void* grad_out, int channels_last, const int64_t* 
                         int64_t P, int reduce, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * P9  fused BatchNorm1d (+ LeakyReLU) of an MLP layer
+ *   replaces core/common_modules/base_modules.py:38-48 (Linear -> FastBatchNorm1d -> LeakyReLU(0.2))
+ *   after the Linear, and FastBatchNorm1d._forward_sparse :139-148: per-column batch statistics
+ *   over ALL rows in training (biased variance for normalisation, unbiased for running_var,
+ *   momentum update), y = act(gamma * (z - mean) * invstd + beta), act(a) = a > 0 ? a : slope * a
+ *   (slope = 1: plain BatchNorm).  z, y [R,C] (dtype); gamma/beta nullable; mean/invstd [C] fp32 are
+ *   written in training and READ in eval (host passes running_mean and rsqrt(running_var + eps)).
+ *   Backward: dz [R,C]; dbeta_dgamma [2,C] fp32 = (sum g ; sum g * zhat) with g = dy * act'.
+ *   workspace: dva_bn_workspace_bytes(R, C) bytes (per-CTA partial sums, deterministic).
+ * ------------------------------------------------------------------------------------------ */
+size_t dva_bn_workspace_bytes(int64_t R, int64_t C);
+int dva_bn_act_fwd(const void* z, const float* gamma, const float* beta, float* running_mean,
+                   float* running_var, float* mean, float* invstd, void* y, int64_t R, int64_t C,
+                   float eps, float momentum, float slope, int training, int dtype, void* workspace,
+                   size_t workspace_bytes, void* stream);
+int dva_bn_act_bwd(const void* dy, const void* z, const float* gamma, const float* beta,
+                   const float* mean, const float* invstd, void* dz, float* dbeta_dgamma, int64_t R,
+                   int64_t C, float slope, int training, int dtype, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Z3  z-buffer visibility from splatting    replaces visibility.py:1073-1195 (CPU/numba oracle)
  *   splat [m,4] int32 (x_a,x_b,y_a,y_b) already clamped, y relative to the un-cropped image;
  *   dist [m] fp32.  Point i wins pixel (x,y) iff dist is the smallest, ties -> lowest i

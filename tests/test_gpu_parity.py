@@ -368,3 +368,40 @@ def test_full_size_properties():
     k = 2000
     exp = att[:k * v].repeat_interleave(C // G, dim=1) * w[:k].repeat_interleave(v, dim=0)
     close(gx[:k * v], exp, 1e-6, "grad_x property")
+
+
+# ------------------------------------------------------------------------------------------------
+# fused BatchNorm + LeakyReLU vs torch (base_modules.py:38-48 semantics)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("R,C", [(5000, 128), (777, 64), (3000, 32), (100, 8), (1, 16), (4099, 33), (20000, 512)])
+def test_bn_act_vs_torch(R, C):
+    from deepviewagg_b200 import ops
+    gen = torch.Generator().manual_seed(R + C)
+    z = (torch.randn(R, C, generator=gen) * 2 + 3).cuda()          # non-zero mean: exercises the shift
+    w = torch.randn(R, C, generator=gen).cuda()
+    for training in (True, False):
+        if R == 1 and training:
+            continue                                              # torch refuses 1 value per channel
+        bn_a = torch.nn.BatchNorm1d(C, momentum=0.1).cuda()
+        bn_b = torch.nn.BatchNorm1d(C, momentum=0.1).cuda()
+        with torch.no_grad():
+            bn_a.weight.copy_(torch.rand(C, generator=gen) + 0.5)
+            bn_a.bias.copy_(torch.randn(C, generator=gen) * 0.3)
+            bn_a.running_mean.copy_(torch.randn(C, generator=gen))
+            bn_a.running_var.copy_(torch.rand(C, generator=gen) + 0.5)
+        bn_b.load_state_dict(bn_a.state_dict())
+        bn_a.train(training), bn_b.train(training)
+        za, zb = z.clone().requires_grad_(True), z.clone().requires_grad_(True)
+        ya = torch.nn.functional.leaky_relu(bn_a(za), 0.2)
+        yb = ops.batch_norm_act(zb, bn_b, negative_slope=0.2)
+        ga = torch.autograd.grad((ya * w).sum(), [za, bn_a.weight, bn_a.bias])
+        gb = torch.autograd.grad((yb * w).sum(), [zb, bn_b.weight, bn_b.bias])
+        close(yb, ya, 2e-5, "bn_act y")
+        for n, a, b in zip(("dz", "dgamma", "dbeta"), gb, ga):
+            # LeakyReLU'(a) is decided by the sign of a ~ 0 for a handful of elements (torch keeps the
+            # sign of its own rounded output): allow isolated flips, bound everything else tightly
+            bad = (a - b).abs() > 2e-4 * max(1.0, float(b.abs().max()))
+            assert int(bad.sum()) <= 4 + a.numel() // 100000, (n, training, int(bad.sum()))
+        close(bn_b.running_mean, bn_a.running_mean, 1e-5, "running_mean")
+        close(bn_b.running_var, bn_a.running_var, 1e-5, "running_var")
+        assert int(bn_b.num_batches_tracked) == int(bn_a.num_batches_tracked)
