@@ -44,7 +44,8 @@ class MLPLayer(nn.Sequential):
             return super().forward(x)
         slope = act.negative_slope if isinstance(act, nn.LeakyReLU) else (0.0 if isinstance(act, nn.ReLU) else 1.0)
         from .. import ops
-        return ops.batch_norm_act(lin(x), bn.batch_norm, negative_slope=slope)
+        z = ops.linear(x, lin.weight) if lin.bias is None else lin(x)   # tcgen05 GEMM when shapes allow
+        return ops.batch_norm_act(z, bn.batch_norm, negative_slope=slope)
 
 
 def MLP(channels, activation=None, bn_momentum=0.1, bias=True):

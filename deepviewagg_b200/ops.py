@@ -505,3 +505,67 @@ def batch_norm_act(z, bn, negative_slope=1.0):
     rm = bn.running_mean if bn.track_running_stats else None
     rv = bn.running_var if bn.track_running_stats else None
     return _BNAct.apply(z, bn.weight, bn.bias, rm, rv, training, momentum, bn.eps, negative_slope)
+
+
+# --------------------------------------------------------------------------------------------
+# dense projection of the MLP layers on tcgen05 tensor cores (base_modules.py:42)
+# --------------------------------------------------------------------------------------------
+_GEMM_PRECISION = {"mode": 0}   # 0: fast-FP32 (9 x BF16, parity mode), 1: TF32
+
+
+def set_gemm_precision(mode):
+    """'fp32' (default; 9xBF16 split products, fp32-grade accuracy) or 'tf32'."""
+    _GEMM_PRECISION["mode"] = {"fp32": 0, "tf32": 1}[mode]
+
+
+def _tc_gemm(a, b, layout, n_out):
+    """layout 0: D[M,n_out] = a[M,K] . b[n_out,K]^T;  1: D[M,n_out] = a[M,K] . b[K,n_out];
+    2: D[N,n_out] = a[M,N]^T . b[M,n_out]  -- through dva_linear_gemm."""
+    lib = _lib.load()
+    prec = _GEMM_PRECISION["mode"]
+    if layout == 2:
+        M, N = a.shape
+        K = n_out
+        out = torch.empty((N, K), dtype=torch.float32, device=a.device)
+    else:
+        M, K = a.shape
+        N = n_out
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    ws_bytes = int(lib.dva_linear_gemm_workspace_bytes(M, N, K, layout, prec))
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib.dva_linear_gemm(ptr(a), ptr(b), ptr(out), M, N, K, layout, prec, ptr(ws), ws.numel(),
+                                  stream_ptr()), "dva_linear_gemm")
+    return out
+
+
+def tc_gemm_supported(x, weight):
+    return (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and x.dim() == 2
+            and x.shape[0] > 0 and x.shape[1] % 4 == 0 and weight.shape[0] % 4 == 0)
+
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight):
+        require_cuda(x, weight)
+        x, w = x.contiguous(), weight.contiguous()
+        ctx.save_for_backward(x, w)
+        return _tc_gemm(x, w, 0, w.shape[0])
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gz):
+        x, w = ctx.saved_tensors
+        gz = gz.contiguous()
+        gx = _tc_gemm(gz, w, 1, w.shape[1]) if ctx.needs_input_grad[0] else None
+        # dW = dZ^T X: [out,in] result reduced over all rows -- stream-K split over the SMs
+        gw = _tc_gemm(gz, x, 2, x.shape[1]) if ctx.needs_input_grad[1] else None
+        return gx, gw
+
+
+def linear(x, weight):
+    """x @ weight.T for a bias-free nn.Linear weight [out, in] (base_modules.py:42) on the tensor
+    cores; shapes the TMA path cannot take (K or N not a multiple of 4, non-fp32) use F.linear."""
+    if not tc_gemm_supported(x, weight):
+        return torch.nn.functional.linear(x, weight)
+    return _Linear.apply(x, weight)

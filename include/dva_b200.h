@@ -152,6 +152,20 @@ int dva_gather_pool_bwd(const void* grad_out, int channels_last, const int64_t* 
                         int64_t P, int reduce, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * P9  dense projection GEMM of an MLP layer (tcgen05 / TMA / TMEM)
+ *   replaces the nn.Linear(bias=False) of base_modules.py:42 in every pool MLP.
+ *   layout 0: D[M,N] = A[M,K] . B[N,K]^T   (forward,  B = weight [out,in])
+ *   layout 1: D[M,N] = A[M,K] . B[K,N]     (backward, dX = dZ . weight)
+ *   layout 2: D[N,K] = A[M,N]^T . B[M,K]   (backward, dW = dZ^T . X; stream-K over the M rows)
+ *   precision 0: fast-FP32 (9 x BF16 split products, fp32-grade accuracy); 1: TF32.
+ *   fp32 row-major operands, 16-byte aligned, N % 4 == 0 and K % 4 == 0 (else DVA_EUNSUPPORTED:
+ *   the host falls back to a library GEMM).  workspace: dva_linear_gemm_workspace_bytes().
+ * ------------------------------------------------------------------------------------------ */
+size_t dva_linear_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int layout, int precision);
+int dva_linear_gemm(const float* A, const float* B, float* D, int64_t M, int64_t N, int64_t K, int layout,
+                    int precision, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * P9  fused BatchNorm1d (+ LeakyReLU) of an MLP layer
  *   replaces core/common_modules/base_modules.py:38-48 (Linear -> FastBatchNorm1d -> LeakyReLU(0.2))
  *   after the Linear, and FastBatchNorm1d._forward_sparse :139-148: per-column batch statistics

@@ -405,3 +405,33 @@ def test_bn_act_vs_torch(R, C):
         close(bn_b.running_mean, bn_a.running_mean, 1e-5, "running_mean")
         close(bn_b.running_var, bn_a.running_var, 1e-5, "running_var")
         assert int(bn_b.num_batches_tracked) == int(bn_a.num_batches_tracked)
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 projection GEMM vs an fp64 matmul
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,K,N", [(4096, 128, 128), (1000, 64, 64), (37, 8, 32), (50000, 128, 64), (3000, 512, 512),
+                                   (129, 32, 4), (1, 16, 16)])
+def test_tc_linear_vs_fp64(M, K, N):
+    from deepviewagg_b200 import ops
+    gen = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=gen).cuda().requires_grad_(True)
+    w = (torch.randn(N, K, generator=gen) / math.sqrt(K)).cuda().requires_grad_(True)
+    g = torch.randn(M, N, generator=gen).cuda()
+    ref = x.double() @ w.double().t()
+    ref_gx = g.double() @ w.double()
+    ref_gw = g.double().t() @ x.double()
+    for mode, tol in (("fp32", 2e-6), ("tf32", 2e-3)):
+        ops.set_gemm_precision(mode)
+        try:
+            y = ops.linear(x, w)
+            gx, gw = torch.autograd.grad((y * g).sum(), [x, w])
+        finally:
+            ops.set_gemm_precision("fp32")
+        close(y, ref, tol, f"linear {mode}")
+        close(gx, ref_gx, tol, f"linear grad_x {mode}")
+        close(gw, ref_gw, tol, f"linear grad_w {mode}")
+    # shapes the TMA kernel cannot take fall back to the library GEMM, same values
+    x2 = torch.randn(100, 33, generator=gen).cuda()
+    w2 = torch.randn(32, 33, generator=gen).cuda()
+    close(ops.linear(x2, w2), x2 @ w2.t(), 1e-6, "fallback")
