@@ -72,18 +72,29 @@ bn_stats_kernel(const T* __restrict__ z, float* __restrict__ partial, int64_t R,
 }
 
 // ---- finalize (fwd): mean / invstd, running statistics (momentum, unbiased variance) --------------
+// one warp per column: lanes stride over the CTA partials (fixed order -> deterministic), fp64 combine
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 template <typename T>
-__global__ void bn_finalize_kernel(const T* __restrict__ z, const float* __restrict__ partial, int grid,
-                                   int64_t R, int C, float eps, float momentum, float* __restrict__ mean,
-                                   float* __restrict__ invstd, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const T* __restrict__ z, const float* __restrict__ partial, int grid,
+                   int64_t R, int C, float eps, float momentum, float* __restrict__ mean,
+                   float* __restrict__ invstd, float* __restrict__ running_mean,
+                   float* __restrict__ running_var) {
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
   double s = 0.0, q = 0.0;
-  for (int b = 0; b < grid; ++b) {
+  for (int b = lane; b < grid; b += 32) {
     s += (double)partial[(int64_t)b * 2 * C + c];
     q += (double)partial[(int64_t)b * 2 * C + C + c];
   }
+  s = warp_sum_d(s); q = warp_sum_d(q);
+  if (lane != 0) return;
   const double n = (double)R, shift = (double)Cvt<T>::to_f(z[c]);
   const double ms = s / n;
   double var = q / n - ms * ms;
@@ -186,13 +197,15 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ z, const fl
 }
 
 // sums[0][c] = sum g (= d beta), sums[1][c] = sum g*zhat (= d gamma)
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int grid, int C,
-                                       float* __restrict__ sums) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(const float* __restrict__ partial, int grid, int C, float* __restrict__ sums) {
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= 2 * C) return;
   double acc = 0.0;
-  for (int b = 0; b < grid; ++b) acc += (double)partial[(int64_t)b * 2 * C + c];
-  sums[c] = (float)acc;
+  for (int b = lane; b < grid; b += 32) acc += (double)partial[(int64_t)b * 2 * C + c];
+  acc = warp_sum_d(acc);
+  if (lane == 0) sums[c] = (float)acc;
 }
 
 // ---- pass 2 (bwd): dz = gamma*invstd * (g - mean(g) - zhat * mean(g*zhat))   [train]
@@ -305,7 +318,7 @@ extern "C" int dva_bn_act_fwd(const void* z, const float* gamma, const float* be
         bn_stats_kernel<T, 1><<<grid, kBnThreads, smem, st>>>((const T*)z, (float*)workspace, R, (int)C);
       }
       if ((rc = check_launch("bn_stats"))) return rc;
-      bn_finalize_kernel<T><<<(int)((C + 127) / 128), 128, 0, st>>>((const T*)z, (const float*)workspace, grid, R,
+      bn_finalize_kernel<T><<<(int)((C + 7) / 8), 256, 0, st>>>((const T*)z, (const float*)workspace, grid, R,
                                                                    (int)C, eps, momentum, mean, invstd,
                                                                    running_mean, running_var);
       if ((rc = check_launch("bn_finalize"))) return rc;
@@ -353,7 +366,7 @@ extern "C" int dva_bn_act_bwd(const void* dy, const void* z, const float* gamma,
     }
     if ((rc = check_launch("bn_bwd_reduce"))) return rc;
     // dgamma_dbeta = [sum g ; sum g*zhat]  (note the order: [0] = d beta, [1] = d gamma)
-    bn_bwd_finalize_kernel<<<(int)((2 * C + 127) / 128), 128, 0, st>>>((const float*)workspace, grid, (int)C, dgamma_dbeta);
+    bn_bwd_finalize_kernel<<<(int)((2 * C + 7) / 8), 256, 0, st>>>((const float*)workspace, grid, (int)C, dgamma_dbeta);
     if ((rc = check_launch("bn_bwd_finalize"))) return rc;
     if (vec > 1)
       bn_bwd_apply_kernel<T, Vec16<T>::N><<<bn_grid_stream(R, (int)C, Vec16<T>::N), kBnThreads, 0, st>>>(

@@ -578,13 +578,17 @@ view_attention_bwd_kernel(const VAParams P) {
   }
 }
 
+// one warp per output (2G <= 64 outputs): lanes stride over the CTA partials in a fixed order
 __global__ void gate_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out,
                                    int blocks, int twoG) {
-  const int j = threadIdx.x;
-  if (j >= twoG) return;
-  float acc = 0.f;
-  for (int b = 0; b < blocks; ++b) acc += partial[(int64_t)b * twoG + j];
-  out[j] = acc;
+  const int lane = threadIdx.x & 31;
+  for (int j = threadIdx.x >> 5; j < twoG; j += blockDim.x >> 5) {
+    float acc = 0.f;
+    for (int b = lane; b < blocks; b += 32) acc += partial[(int64_t)b * twoG + j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[j] = acc;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -780,7 +784,7 @@ extern "C" int dva_view_attention_bwd(const void* x, const void* idx, int idx_is
   }
   if (rc) return rc;
   if (gating) {
-    gate_reduce_kernel<<<1, 64, 0, st>>>(P.gate_partial, grad_gate, grid, 2 * (int)G);
+    gate_reduce_kernel<<<1, 1024, 0, st>>>(P.gate_partial, grad_gate, grid, 2 * (int)G);
     return check_launch("gate_reduce");
   }
   return DVA_OK;
