@@ -46,6 +46,10 @@ SIGNATURES = {
                                    _i64, _i64, _i32, _i32, _vp]),
     "dva_gather_pool_bwd": (_i32, [_vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _i64,
                                    _i64, _i64, _i32, _i32, _vp]),
+    "dva_interp_pool_fwd": (_i32, [_vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _i64,
+                                   _i64, _i64, _i64, _i64, _i32, _i32, _vp]),
+    "dva_interp_pool_bwd": (_i32, [_vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _i64,
+                                   _i64, _i64, _i64, _i64, _i32, _i32, _vp]),
     "dva_linear_gemm_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32, _i32]),
     "dva_linear_gemm": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _sz, _vp]),
     "dva_bn_workspace_bytes": (_sz, [_i64, _i64]),

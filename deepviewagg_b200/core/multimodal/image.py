@@ -499,6 +499,10 @@ class SameSettingImageData:
         scale = 1 / self.downscale
         mappings = self.scaled_mappings(interpolate)
         if interpolate and scale != 1:
+            if self.x.is_cuda:   # bilinear corners read straight from the map, no padded copy
+                from ... import ops
+                return ops.sparse_interpolation_pixels(self.x, mappings.feature_map_indexing[0],
+                                                       mappings.pixels, self.mapping_size)
             resolution = torch.tensor([self.mapping_size], dtype=torch.float, device=self.device)
             coords = (mappings.pixels / (resolution - 1))[:, [1, 0]]
             return sparse_interpolation(self.x, coords, mappings.feature_map_indexing[0])

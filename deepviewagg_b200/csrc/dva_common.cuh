@@ -22,6 +22,11 @@ inline int fail(int code, const char* msg) {
   return code;
 }
 
+template <typename... A> inline int failf(int code, const char* fmt, A... a) {
+  snprintf(tls_error_buf(), 256, fmt, a...);
+  return code;
+}
+
 inline int check_launch(const char* what) {
   launch_counter().fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();

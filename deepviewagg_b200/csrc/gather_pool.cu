@@ -7,16 +7,51 @@
 // warp reads 32 consecutive channels per pixel (coalesced); with the reference's NCHW layout
 // every element is H*W apart (32-byte sector per 4-byte element) -- supported for drop-in use,
 // channels-last is the fast path.
+//
+// INTERP: the `interpolate=True` branch of get_mapped_features (image.py:1278-1283 ->
+// sparse_interpolation, image.py:105-170): pixels live at the mapping resolution (map_w, map_h),
+// the feature map is smaller, and every pixel reads 4 bilinear corners of the replicate-padded
+// map.  The fp32 arithmetic follows the reference operation by operation (no FMA contraction),
+// so corner choices, values and therefore max / argmax decisions are identical in fp32.
 #include "dva_common.cuh"
 
 namespace dva {
 
-template <typename T, typename PIX, bool CL, int RED>
+// Bilinear footprint of one mapping pixel (image.py:145-163).
+struct Bilin {
+  int r0, r1, c0, c1;          // clamped source rows / columns (replicate padding, image.py:133)
+  float w00, w01, w10, w11;    // tl, tr, bl, br
+};
+__device__ __forceinline__ Bilin bilin_setup(int px, int py, int H, int W, float mw1, float mh1) {
+  // coords = pixels / (resolution - 1), (x,y) -> (row, col)       image.py:1280-1281
+  const float cy = __fdiv_rn((float)py, mh1), cx = __fdiv_rn((float)px, mw1);
+  // pixels = coords * (h, w) + 0.5 in the padded frame               image.py:143
+  const float p0 = __fadd_rn(__fmul_rn(cy, (float)H), 0.5f);
+  const float p1 = __fadd_rn(__fmul_rn(cx, (float)W), 0.5f);
+  const float top = floorf(p0), bottom = floorf(__fadd_rn(p0, 1.f));
+  const float left = floorf(p1), right = floorf(__fadd_rn(p1, 1.f));
+  const float dyt = __fsub_rn(p0, bottom), dyb = __fsub_rn(p0, top);   // weight of top / bottom row
+  const float dxl = __fsub_rn(p1, right), dxr = __fsub_rn(p1, left);
+  Bilin b;
+  b.w00 = fabsf(__fmul_rn(dyt, dxl)); b.w01 = fabsf(__fmul_rn(dyt, dxr));
+  b.w10 = fabsf(__fmul_rn(dyb, dxl)); b.w11 = fabsf(__fmul_rn(dyb, dxr));
+  b.r0 = min(max((int)top - 1, 0), H - 1); b.r1 = min(max((int)bottom - 1, 0), H - 1);
+  b.c0 = min(max((int)left - 1, 0), W - 1); b.c1 = min(max((int)right - 1, 0), W - 1);
+  return b;
+}
+
+template <bool CL>
+__device__ __forceinline__ int64_t fmap_off(int64_t b, int64_t c, int64_t y, int64_t x, int64_t C,
+                                            int64_t H, int64_t W) {
+  return CL ? (((b * H + y) * W + x) * C + c) : (((b * C + c) * H + y) * W + x);
+}
+
+template <typename T, typename PIX, bool CL, int RED, bool INTERP>
 __global__ void __launch_bounds__(256)
 gather_pool_fwd_kernel(const T* __restrict__ fmap, const int64_t* __restrict__ img,
                        const PIX* __restrict__ pix, const int64_t* __restrict__ aptr,
                        T* __restrict__ out, int64_t* __restrict__ arg, int64_t C, int64_t H,
-                       int64_t W, int64_t Vw, int64_t P) {
+                       int64_t W, int64_t Vw, int64_t P, float mw1, float mh1) {
   const int64_t total = Vw * C;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
@@ -27,8 +62,19 @@ gather_pool_fwd_kernel(const T* __restrict__ fmap, const int64_t* __restrict__ i
     int64_t best = P;
     for (int64_t p = p0; p < p1; ++p) {
       const int64_t px = (int64_t)pix[2 * p], py = (int64_t)pix[2 * p + 1];
-      const int64_t off = CL ? (((b * H + py) * W + px) * C + c) : (((b * C + c) * H + py) * W + px);
-      const float v = Cvt<T>::to_f(fmap[off]);
+      float v;
+      if (INTERP) {
+        const Bilin q = bilin_setup((int)px, (int)py, (int)H, (int)W, mw1, mh1);
+        const float f00 = Cvt<T>::to_f(fmap[fmap_off<CL>(b, c, q.r0, q.c0, C, H, W)]);
+        const float f01 = Cvt<T>::to_f(fmap[fmap_off<CL>(b, c, q.r0, q.c1, C, H, W)]);
+        const float f10 = Cvt<T>::to_f(fmap[fmap_off<CL>(b, c, q.r1, q.c0, C, H, W)]);
+        const float f11 = Cvt<T>::to_f(fmap[fmap_off<CL>(b, c, q.r1, q.c1, C, H, W)]);
+        // image.py:165-168: four products summed left to right
+        v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(q.w00, f00), __fmul_rn(q.w01, f01)),
+                                __fmul_rn(q.w10, f10)), __fmul_rn(q.w11, f11));
+      } else {
+        v = Cvt<T>::to_f(fmap[fmap_off<CL>(b, c, py, px, C, H, W)]);
+      }
       if (RED == DVA_SUM || RED == DVA_MEAN) acc += v;
       else if (p == p0 || (RED == DVA_MAX ? v > acc : v < acc)) { acc = v; best = p; }
     }
@@ -38,12 +84,28 @@ gather_pool_fwd_kernel(const T* __restrict__ fmap, const int64_t* __restrict__ i
   }
 }
 
-template <typename T, typename PIX, bool CL, int RED>
+template <bool CL, bool INTERP, typename PIX>
+__device__ __forceinline__ void scatter_pixel(float* __restrict__ gfmap, const PIX* __restrict__ pix,
+                                              int64_t p, int64_t b, int64_t c, int64_t C, int64_t H,
+                                              int64_t W, float mw1, float mh1, float g) {
+  const int64_t px = (int64_t)pix[2 * p], py = (int64_t)pix[2 * p + 1];
+  if (INTERP) {
+    const Bilin q = bilin_setup((int)px, (int)py, (int)H, (int)W, mw1, mh1);
+    atomicAdd(gfmap + fmap_off<CL>(b, c, q.r0, q.c0, C, H, W), q.w00 * g);
+    atomicAdd(gfmap + fmap_off<CL>(b, c, q.r0, q.c1, C, H, W), q.w01 * g);
+    atomicAdd(gfmap + fmap_off<CL>(b, c, q.r1, q.c0, C, H, W), q.w10 * g);
+    atomicAdd(gfmap + fmap_off<CL>(b, c, q.r1, q.c1, C, H, W), q.w11 * g);
+  } else {
+    atomicAdd(gfmap + fmap_off<CL>(b, c, py, px, C, H, W), g);
+  }
+}
+
+template <typename T, typename PIX, bool CL, int RED, bool INTERP>
 __global__ void __launch_bounds__(256)
 gather_pool_bwd_kernel(const T* __restrict__ gout, const int64_t* __restrict__ img,
                        const PIX* __restrict__ pix, const int64_t* __restrict__ aptr,
                        const int64_t* __restrict__ arg, float* __restrict__ gfmap, int64_t C,
-                       int64_t H, int64_t W, int64_t Vw) {
+                       int64_t H, int64_t W, int64_t Vw, float mw1, float mh1) {
   const int64_t total = Vw * C;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
@@ -54,16 +116,9 @@ gather_pool_bwd_kernel(const T* __restrict__ gout, const int64_t* __restrict__ i
     float g = Cvt<T>::to_f(gout[t]);
     if (RED == DVA_MEAN) g /= (float)(p1 - p0);
     if (RED == DVA_MAX || RED == DVA_MIN) {
-      const int64_t p = arg[t];
-      const int64_t px = (int64_t)pix[2 * p], py = (int64_t)pix[2 * p + 1];
-      const int64_t off = CL ? (((b * H + py) * W + px) * C + c) : (((b * C + c) * H + py) * W + px);
-      atomicAdd(gfmap + off, g);
+      scatter_pixel<CL, INTERP>(gfmap, pix, arg[t], b, c, C, H, W, mw1, mh1, g);
     } else {
-      for (int64_t p = p0; p < p1; ++p) {
-        const int64_t px = (int64_t)pix[2 * p], py = (int64_t)pix[2 * p + 1];
-        const int64_t off = CL ? (((b * H + py) * W + px) * C + c) : (((b * C + c) * H + py) * W + px);
-        atomicAdd(gfmap + off, g);
-      }
+      for (int64_t p = p0; p < p1; ++p) scatter_pixel<CL, INTERP>(gfmap, pix, p, b, c, C, H, W, mw1, mh1, g);
     }
   }
 }
@@ -74,12 +129,12 @@ static inline int gp_grid(int64_t total) {
   return (int)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
 }
 
-template <typename T, typename PIX, bool CL>
+template <typename T, typename PIX, bool CL, bool INTERP>
 static int gp_fwd_red(const void* fmap, const int64_t* img, const void* pix, const int64_t* aptr,
                       void* out, int64_t* arg, int64_t C, int64_t H, int64_t W, int64_t Vw,
-                      int64_t P, int reduce, cudaStream_t st) {
+                      int64_t P, float mw1, float mh1, int reduce, cudaStream_t st) {
   const int grid = gp_grid(Vw * C);
-#define GP_F(R) gather_pool_fwd_kernel<T, PIX, CL, R><<<grid, 256, 0, st>>>((const T*)fmap, img, (const PIX*)pix, aptr, (T*)out, arg, C, H, W, Vw, P)
+#define GP_F(R) gather_pool_fwd_kernel<T, PIX, CL, R, INTERP><<<grid, 256, 0, st>>>((const T*)fmap, img, (const PIX*)pix, aptr, (T*)out, arg, C, H, W, Vw, P, mw1, mh1)
   switch (reduce) {
     case DVA_SUM: GP_F(DVA_SUM); break;
     case DVA_MEAN: GP_F(DVA_MEAN); break;
@@ -91,12 +146,12 @@ static int gp_fwd_red(const void* fmap, const int64_t* img, const void* pix, con
   return check_launch("gather_pool_fwd");
 }
 
-template <typename T, typename PIX, bool CL>
+template <typename T, typename PIX, bool CL, bool INTERP>
 static int gp_bwd_red(const void* gout, const int64_t* img, const void* pix, const int64_t* aptr,
                       const int64_t* arg, float* gfmap, int64_t C, int64_t H, int64_t W,
-                      int64_t Vw, int reduce, cudaStream_t st) {
+                      int64_t Vw, float mw1, float mh1, int reduce, cudaStream_t st) {
   const int grid = gp_grid(Vw * C);
-#define GP_B(R) gather_pool_bwd_kernel<T, PIX, CL, R><<<grid, 256, 0, st>>>((const T*)gout, img, (const PIX*)pix, aptr, arg, gfmap, C, H, W, Vw)
+#define GP_B(R) gather_pool_bwd_kernel<T, PIX, CL, R, INTERP><<<grid, 256, 0, st>>>((const T*)gout, img, (const PIX*)pix, aptr, arg, gfmap, C, H, W, Vw, mw1, mh1)
   switch (reduce) {
     case DVA_SUM: GP_B(DVA_SUM); break;
     case DVA_MEAN: GP_B(DVA_MEAN); break;
@@ -112,31 +167,66 @@ static int gp_bwd_red(const void* gout, const int64_t* img, const void* pix, con
 
 using namespace dva;
 
-#define GP_DISPATCH(FN, ...)                                                              \
+#define GP_DISPATCH(FN, INTERP, ...)                                                      \
   do {                                                                                    \
     if (channels_last) {                                                                  \
-      if (pix_is_i16) return FN<T, int16_t, true>(__VA_ARGS__);                           \
-      return FN<T, int32_t, true>(__VA_ARGS__);                                           \
+      if (pix_is_i16) return FN<T, int16_t, true, INTERP>(__VA_ARGS__);                   \
+      return FN<T, int32_t, true, INTERP>(__VA_ARGS__);                                   \
     }                                                                                     \
-    if (pix_is_i16) return FN<T, int16_t, false>(__VA_ARGS__);                            \
-    return FN<T, int32_t, false>(__VA_ARGS__);                                            \
+    if (pix_is_i16) return FN<T, int16_t, false, INTERP>(__VA_ARGS__);                    \
+    return FN<T, int32_t, false, INTERP>(__VA_ARGS__);                                    \
   } while (0)
+
+template <bool INTERP>
+static int gather_pool_fwd_impl(const char* who, const void* fmap, int channels_last, const int64_t* img,
+                                const void* pix, int pix_is_i16, const int64_t* aptr, void* out,
+                                int64_t* arg, int64_t B, int64_t C, int64_t H, int64_t W,
+                                int64_t map_w, int64_t map_h, int64_t Vw, int64_t P, int reduce,
+                                int dtype, void* stream) {
+  if (B < 0 || C < 0 || H < 0 || W < 0 || Vw < 0 || P < 0) return failf(DVA_EINVAL, "%s: negative size", who);
+  if (Vw == 0 || C == 0) return DVA_OK;
+  if (!aptr || !out || !img || (P > 0 && (!fmap || !pix))) return failf(DVA_EINVAL, "%s: null pointer", who);
+  if (INTERP && (map_w < 2 || map_h < 2 || H < 1 || W < 1 || H > (1 << 24) || W > (1 << 24)))
+    return failf(DVA_EINVAL, "%s: bad map / mapping size", who);
+  const float mw1 = (float)(map_w - 1), mh1 = (float)(map_h - 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case DVA_F32: { using T = float; GP_DISPATCH(gp_fwd_red, INTERP, fmap, img, pix, aptr, out, arg, C, H, W, Vw, P, mw1, mh1, reduce, st); }
+    case DVA_BF16: { using T = __nv_bfloat16; GP_DISPATCH(gp_fwd_red, INTERP, fmap, img, pix, aptr, out, arg, C, H, W, Vw, P, mw1, mh1, reduce, st); }
+    case DVA_F16: { using T = __half; GP_DISPATCH(gp_fwd_red, INTERP, fmap, img, pix, aptr, out, arg, C, H, W, Vw, P, mw1, mh1, reduce, st); }
+    default: return failf(DVA_EINVAL, "%s: unknown dtype", who);
+  }
+}
+
+template <bool INTERP>
+static int gather_pool_bwd_impl(const char* who, const void* grad_out, int channels_last,
+                                const int64_t* img, const void* pix, int pix_is_i16,
+                                const int64_t* aptr, const int64_t* arg, float* grad_fmap, int64_t B,
+                                int64_t C, int64_t H, int64_t W, int64_t map_w, int64_t map_h,
+                                int64_t Vw, int64_t P, int reduce, int dtype, void* stream) {
+  if (B < 0 || C < 0 || H < 0 || W < 0 || Vw < 0 || P < 0) return failf(DVA_EINVAL, "%s: negative size", who);
+  if (Vw == 0 || C == 0 || P == 0) return DVA_OK;
+  if (!aptr || !grad_out || !img || !pix || !grad_fmap) return failf(DVA_EINVAL, "%s: null pointer", who);
+  if ((reduce == DVA_MAX || reduce == DVA_MIN) && !arg) return failf(DVA_EINVAL, "%s: max/min need arg", who);
+  if (INTERP && (map_w < 2 || map_h < 2 || H < 1 || W < 1 || H > (1 << 24) || W > (1 << 24)))
+    return failf(DVA_EINVAL, "%s: bad map / mapping size", who);
+  const float mw1 = (float)(map_w - 1), mh1 = (float)(map_h - 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case DVA_F32: { using T = float; GP_DISPATCH(gp_bwd_red, INTERP, grad_out, img, pix, aptr, arg, grad_fmap, C, H, W, Vw, mw1, mh1, reduce, st); }
+    case DVA_BF16: { using T = __nv_bfloat16; GP_DISPATCH(gp_bwd_red, INTERP, grad_out, img, pix, aptr, arg, grad_fmap, C, H, W, Vw, mw1, mh1, reduce, st); }
+    case DVA_F16: { using T = __half; GP_DISPATCH(gp_bwd_red, INTERP, grad_out, img, pix, aptr, arg, grad_fmap, C, H, W, Vw, mw1, mh1, reduce, st); }
+    default: return failf(DVA_EINVAL, "%s: unknown dtype", who);
+  }
+}
 
 extern "C" int dva_gather_pool_fwd(const void* fmap, int channels_last, const int64_t* img,
                                    const void* pix, int pix_is_i16, const int64_t* aptr,
                                    void* out, int64_t* arg, int64_t B, int64_t C, int64_t H,
                                    int64_t W, int64_t Vw, int64_t P, int reduce, int dtype,
                                    void* stream) {
-  if (B < 0 || C < 0 || H < 0 || W < 0 || Vw < 0 || P < 0) return fail(DVA_EINVAL, "gather_pool_fwd: negative size");
-  if (Vw == 0 || C == 0) return DVA_OK;
-  if (!aptr || !out || !img || (P > 0 && (!fmap || !pix))) return fail(DVA_EINVAL, "gather_pool_fwd: null pointer");
-  cudaStream_t st = (cudaStream_t)stream;
-  switch (dtype) {
-    case DVA_F32: { using T = float; GP_DISPATCH(gp_fwd_red, fmap, img, pix, aptr, out, arg, C, H, W, Vw, P, reduce, st); }
-    case DVA_BF16: { using T = __nv_bfloat16; GP_DISPATCH(gp_fwd_red, fmap, img, pix, aptr, out, arg, C, H, W, Vw, P, reduce, st); }
-    case DVA_F16: { using T = __half; GP_DISPATCH(gp_fwd_red, fmap, img, pix, aptr, out, arg, C, H, W, Vw, P, reduce, st); }
-    default: return fail(DVA_EINVAL, "gather_pool_fwd: unknown dtype");
-  }
+  return gather_pool_fwd_impl<false>("gather_pool_fwd", fmap, channels_last, img, pix, pix_is_i16, aptr,
+                                     out, arg, B, C, H, W, 0, 0, Vw, P, reduce, dtype, stream);
 }
 
 extern "C" int dva_gather_pool_bwd(const void* grad_out, int channels_last, const int64_t* img,
@@ -144,15 +234,24 @@ extern "C" int dva_gather_pool_bwd(const void* grad_out, int channels_last, cons
                                    const int64_t* arg, float* grad_fmap, int64_t B, int64_t C,
                                    int64_t H, int64_t W, int64_t Vw, int64_t P, int reduce,
                                    int dtype, void* stream) {
-  if (B < 0 || C < 0 || H < 0 || W < 0 || Vw < 0 || P < 0) return fail(DVA_EINVAL, "gather_pool_bwd: negative size");
-  if (Vw == 0 || C == 0 || P == 0) return DVA_OK;
-  if (!aptr || !grad_out || !img || !pix || !grad_fmap) return fail(DVA_EINVAL, "gather_pool_bwd: null pointer");
-  if ((reduce == DVA_MAX || reduce == DVA_MIN) && !arg) return fail(DVA_EINVAL, "gather_pool_bwd: max/min need arg");
-  cudaStream_t st = (cudaStream_t)stream;
-  switch (dtype) {
-    case DVA_F32: { using T = float; GP_DISPATCH(gp_bwd_red, grad_out, img, pix, aptr, arg, grad_fmap, C, H, W, Vw, reduce, st); }
-    case DVA_BF16: { using T = __nv_bfloat16; GP_DISPATCH(gp_bwd_red, grad_out, img, pix, aptr, arg, grad_fmap, C, H, W, Vw, reduce, st); }
-    case DVA_F16: { using T = __half; GP_DISPATCH(gp_bwd_red, grad_out, img, pix, aptr, arg, grad_fmap, C, H, W, Vw, reduce, st); }
-    default: return fail(DVA_EINVAL, "gather_pool_bwd: unknown dtype");
-  }
+  return gather_pool_bwd_impl<false>("gather_pool_bwd", grad_out, channels_last, img, pix, pix_is_i16,
+                                     aptr, arg, grad_fmap, B, C, H, W, 0, 0, Vw, P, reduce, dtype, stream);
+}
+
+extern "C" int dva_interp_pool_fwd(const void* fmap, int channels_last, const int64_t* img,
+                                   const void* pix, int pix_is_i16, const int64_t* aptr,
+                                   void* out, int64_t* arg, int64_t B, int64_t C, int64_t H,
+                                   int64_t W, int64_t map_w, int64_t map_h, int64_t Vw, int64_t P,
+                                   int reduce, int dtype, void* stream) {
+  return gather_pool_fwd_impl<true>("interp_pool_fwd", fmap, channels_last, img, pix, pix_is_i16, aptr,
+                                    out, arg, B, C, H, W, map_w, map_h, Vw, P, reduce, dtype, stream);
+}
+
+extern "C" int dva_interp_pool_bwd(const void* grad_out, int channels_last, const int64_t* img,
+                                   const void* pix, int pix_is_i16, const int64_t* aptr,
+                                   const int64_t* arg, float* grad_fmap, int64_t B, int64_t C,
+                                   int64_t H, int64_t W, int64_t map_w, int64_t map_h, int64_t Vw,
+                                   int64_t P, int reduce, int dtype, void* stream) {
+  return gather_pool_bwd_impl<true>("interp_pool_bwd", grad_out, channels_last, img, pix, pix_is_i16,
+                                    aptr, arg, grad_fmap, B, C, H, W, map_w, map_h, Vw, P, reduce, dtype, stream);
 }

@@ -208,13 +208,18 @@ class UnimodalBranch(nn.Module):
     def _atomic_one(self, x_3d, im):
         """[V_s, C] view features of one setting."""
         fused = isinstance(self.atomic_pool, BimodalCSRPool) and not self.atomic_pool.save_last \
-            and not self.interpolate and im.x.is_cuda
+            and im.x.is_cuda
         if fused:
-            # pixel gather + pool in one kernel; a channels_last feature map is read coalesced
-            maps = im.scaled_mappings(interpolate=False)
+            # pixel gather (or bilinear interpolation) + pool in one kernel; a channels_last
+            # feature map is read coalesced
+            bilinear = self.interpolate and im.downscale != 1
+            maps = im.scaled_mappings(interpolate=self.interpolate)
             x = im.x
             cl = x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
             fmap = x.permute(0, 2, 3, 1) if cl else x
+            if bilinear:
+                return ops.interp_pool(fmap, maps.images, maps.pixels, maps.atomic_csr_indexing,
+                                       im.mapping_size, reduce=self.atomic_pool._mode, channels_last=cl)
             return ops.gather_pool(fmap, maps.images, maps.pixels, maps.atomic_csr_indexing,
                                    reduce=self.atomic_pool._mode, channels_last=cl)
         x_pix = im.get_mapped_features(interpolate=self.interpolate)

@@ -390,7 +390,7 @@ def heuristic_pool(x_mod, x_map, csr_idx, feat, mode="max"):
 # --------------------------------------------------------------------------------------------
 class _GatherPool(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, fmap, images, pixels, atomic_ptr, reduce, channels_last):
+    def forward(ctx, fmap, images, pixels, atomic_ptr, reduce, channels_last, mapping_size):
         require_cuda(fmap, images, pixels, atomic_ptr)
         lib = _lib.load()
         fmap = fmap.contiguous()
@@ -406,12 +406,16 @@ class _GatherPool(torch.autograd.Function):
         Vw, P, code = atomic_ptr.numel() - 1, pixels.shape[0], REDUCE_CODES[reduce]
         out = torch.empty((Vw, C), dtype=fmap.dtype, device=fmap.device)
         arg = torch.empty((Vw, C), dtype=torch.int64, device=fmap.device) if code in (2, 3) else None
+        head = (ptr(fmap), int(channels_last), ptr(images), ptr(pixels), int(pixels.dtype == torch.int16),
+                ptr(atomic_ptr), ptr(out), ptr(arg), B, C, H, W)
+        tail = (Vw, P, code, dtype_code(fmap), stream_ptr())
         with torch.cuda.device(fmap.device):
-            check(lib.dva_gather_pool_fwd(ptr(fmap), int(channels_last), ptr(images), ptr(pixels),
-                                          int(pixels.dtype == torch.int16), ptr(atomic_ptr), ptr(out),
-                                          ptr(arg), B, C, H, W, Vw, P, code, dtype_code(fmap),
-                                          stream_ptr()), "dva_gather_pool_fwd")
-        ctx.cfg = (B, C, H, W, Vw, P, code, bool(channels_last), fmap.shape, fmap.dtype)
+            if mapping_size is None:
+                check(lib.dva_gather_pool_fwd(*head, *tail), "dva_gather_pool_fwd")
+            else:
+                check(lib.dva_interp_pool_fwd(*head, int(mapping_size[0]), int(mapping_size[1]), *tail),
+                      "dva_interp_pool_fwd")
+        ctx.cfg = (B, C, H, W, Vw, P, code, bool(channels_last), fmap.shape, fmap.dtype, mapping_size)
         ctx.save_for_backward(images, pixels, atomic_ptr, arg)
         return out
 
@@ -419,21 +423,42 @@ class _GatherPool(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
         images, pixels, atomic_ptr, arg = ctx.saved_tensors
-        B, C, H, W, Vw, P, code, cl, shape, dt = ctx.cfg
+        B, C, H, W, Vw, P, code, cl, shape, dt, mapping_size = ctx.cfg
         lib = _lib.load()
         grad_out = grad_out.contiguous()
         gf = torch.zeros(shape, dtype=torch.float32, device=grad_out.device)
+        head = (ptr(grad_out), int(cl), ptr(images), ptr(pixels), int(pixels.dtype == torch.int16),
+                ptr(atomic_ptr), ptr(arg), ptr(gf), B, C, H, W)
+        tail = (Vw, P, code, dtype_code(grad_out), stream_ptr())
         with torch.cuda.device(grad_out.device):
-            check(lib.dva_gather_pool_bwd(ptr(grad_out), int(cl), ptr(images), ptr(pixels),
-                                          int(pixels.dtype == torch.int16), ptr(atomic_ptr), ptr(arg),
-                                          ptr(gf), B, C, H, W, Vw, P, code, dtype_code(grad_out),
-                                          stream_ptr()), "dva_gather_pool_bwd")
-        return gf.to(dt), None, None, None, None, None
+            if mapping_size is None:
+                check(lib.dva_gather_pool_bwd(*head, *tail), "dva_gather_pool_bwd")
+            else:
+                check(lib.dva_interp_pool_bwd(*head, int(mapping_size[0]), int(mapping_size[1]), *tail),
+                      "dva_interp_pool_bwd")
+        return gf.to(dt), None, None, None, None, None, None
 
 
 def gather_pool(fmap, images, pixels, atomic_ptr, reduce="max", channels_last=False):
     """segment_csr(fmap[(images_per_pixel, :, py, px)], atomic_ptr, reduce) without the [P,C] copy."""
-    return _GatherPool.apply(fmap, images, pixels, atomic_ptr, reduce, channels_last)
+    return _GatherPool.apply(fmap, images, pixels, atomic_ptr, reduce, channels_last, None)
+
+
+def interp_pool(fmap, images, pixels, atomic_ptr, mapping_size, reduce="max", channels_last=False):
+    """segment_csr(sparse_interpolation(fmap, pixels / (mapping_size - 1), images_per_pixel),
+    atomic_ptr, reduce) (image.py:1278-1283 + pooling.py:63) in one kernel.  `pixels` are (x, y)
+    at the mapping resolution `mapping_size` = (W_map, H_map); padding mode 'border'."""
+    return _GatherPool.apply(fmap, images, pixels, atomic_ptr, reduce, channels_last,
+                             (int(mapping_size[0]), int(mapping_size[1])))
+
+
+def sparse_interpolation_pixels(fmap, images_per_pixel, pixels, mapping_size, channels_last=False):
+    """Per-pixel bilinear features [P, C] (image.py:1278-1283): the pooled kernel with one pixel per
+    segment."""
+    P = pixels.shape[0]
+    aptr = torch.arange(P + 1, dtype=torch.int64, device=fmap.device)
+    return _GatherPool.apply(fmap, images_per_pixel, pixels, aptr, "sum", channels_last,
+                             (int(mapping_size[0]), int(mapping_size[1])))
 
 
 # --------------------------------------------------------------------------------------------

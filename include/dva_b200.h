@@ -151,6 +151,22 @@ int dva_gather_pool_bwd(const void* grad_out, int channels_last, const int64_t* 
                         float* grad_fmap, int64_t B, int64_t C, int64_t H, int64_t W, int64_t Vw,
                         int64_t P, int reduce, int dtype, void* stream);
 
+/* I5b  bilinear variant: the `interpolate=True` branch of get_mapped_features
+ *   replaces image.py:1278-1283 -> sparse_interpolation (image.py:105-170, padding 'border')
+ *   followed by the same atomic pool.  pix are at the MAPPING resolution (map_w, map_h); every
+ *   pixel reads the 4 bilinear corners of the replicate-padded [H,W] map.  The fp32 operation
+ *   order is the reference's, so fp32 results (and max / argmax choices) are identical.
+ *   A per-pixel interpolation without pooling is aptr = 0..P with reduce = DVA_SUM. */
+int dva_interp_pool_fwd(const void* fmap, int channels_last, const int64_t* img, const void* pix,
+                        int pix_is_i16, const int64_t* aptr, void* out, int64_t* arg,
+                        int64_t B, int64_t C, int64_t H, int64_t W, int64_t map_w, int64_t map_h,
+                        int64_t Vw, int64_t P, int reduce, int dtype, void* stream);
+int dva_interp_pool_bwd(const void* grad_out, int channels_last, const int64_t* img,
+                        const void* pix, int pix_is_i16, const int64_t* aptr, const int64_t* arg,
+                        float* grad_fmap, int64_t B, int64_t C, int64_t H, int64_t W,
+                        int64_t map_w, int64_t map_h, int64_t Vw, int64_t P, int reduce, int dtype,
+                        void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * P9  dense projection GEMM of an MLP layer (tcgen05 / TMA / TMEM)
  *   replaces the nn.Linear(bias=False) of base_modules.py:42 in every pool MLP.

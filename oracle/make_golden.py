@@ -190,6 +190,8 @@ def main():
 
     make_integer_golden(ref)
     make_branch_golden(ref)
+    make_branch_golden(ref, interpolate=True, name="unimodal_branch_interp")
+    make_interp_golden(ref)
     make_camera_golden(ref)
 
 
@@ -263,7 +265,7 @@ def toy_settings(gen, n_points, specs, F=8):
     return out
 
 
-def make_branch_golden(ref):
+def make_branch_golden(ref, interpolate=False, name="unimodal_branch_toy"):
     """config #0 ("toy: 1k points x 4 views, CPU forward through the DeepViewAgg module"): the
     reference's UnimodalBranch (modules.py:249-566) on a two-setting ImageData, atomic max pool,
     GroupBimodalCSRPool view pool, concatenation fusion; forward + gradients."""
@@ -295,7 +297,8 @@ def make_branch_golden(ref):
         for k, p in view_pool.named_parameters():
             if "batch_norm" in k or k.startswith("G."):
                 p.add_(0.3 * torch.randn(p.shape, generator=gen))
-    branch = M.UnimodalBranch(None, P.BimodalCSRPool(mode="max"), view_pool, ref.fusion.BimodalFusion("concatenation"))
+    branch = M.UnimodalBranch(None, P.BimodalCSRPool(mode="max"), view_pool, ref.fusion.BimodalFusion("concatenation"),
+                              interpolate=interpolate)
     branch.train()
     x_3d = torch.randn(N, C3, generator=gen).requires_grad_(True)
     w = torch.randn(N, C3 + C, generator=gen)
@@ -305,8 +308,34 @@ def make_branch_golden(ref):
     gs = torch.autograd.grad((out["x_3d"] * w).sum(), [x_3d] + xs + list(params.values()), allow_unused=True)
     names = ["x_3d", "s0_x", "s1_x"] + ["param/" + k for k in params]
     grads = {"grad/" + n: (g if g is not None else torch.zeros(1)) for n, g in zip(names, gs)}
-    save("unimodal_branch_toy", x_3d=x_3d, w=w, out=out["x_3d"], x_seen=out["x_seen"],
+    save(name, x_3d=x_3d, w=w, out=out["x_3d"], x_seen=out["x_seen"],
          csr=mod.view_cat_csr_indexing, n_points=np.array(N), **arrays, **sd0, **grads)
+
+
+def make_interp_golden(ref):
+    """sparse_interpolation (image.py:105-170) through get_mapped_features(interpolate=True)
+    (image.py:1278-1283): pixels at the mapping resolution, maps at 1/2 and 1/4 of it, every
+    border / corner pixel included; output and gradient w.r.t. the maps."""
+    import numpy as np
+    I = ref.image
+    gen = torch.Generator().manual_seed(777)
+    arrays = {}
+    for tag, (W, H, ds, B, C) in {"half": (64, 32, 2, 3, 8), "quarter": (96, 64, 4, 2, 5)}.items():
+        n = 4000
+        pix = torch.stack([torch.randint(0, W, (n,), generator=gen), torch.randint(0, H, (n,), generator=gen)], 1)
+        edge = torch.tensor([[0, 0], [W - 1, 0], [0, H - 1], [W - 1, H - 1], [W // 2, 0], [0, H // 2],
+                             [W - 1, H // 2], [W // 2, H - 1]])
+        pix = torch.cat([edge, pix]).long()
+        batch = torch.randint(0, B, (pix.shape[0],), generator=gen)
+        x = torch.randn(B, C, H // ds, W // ds, generator=gen).requires_grad_(True)
+        resolution = torch.Tensor([[W, H]])
+        coords = (pix / (resolution - 1))[:, [1, 0]]
+        out = I.sparse_interpolation(x, coords, batch)
+        w = torch.randn(out.shape, generator=gen)
+        (gx,) = torch.autograd.grad((out * w).sum(), [x])
+        arrays.update({f"{tag}_pix": pix, f"{tag}_batch": batch, f"{tag}_x": x, f"{tag}_out": out,
+                       f"{tag}_w": w, f"{tag}_gx": gx, f"{tag}_size": np.array([W, H, ds])})
+    save("sparse_interpolation", **arrays)
 
 
 def make_integer_golden(ref):

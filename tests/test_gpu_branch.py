@@ -18,11 +18,14 @@ def _close(a, b, tol, what):
 
 
 @pytest.mark.parametrize("channels_last", [False, True])
-def test_unimodal_branch_vs_reference(channels_last):
+@pytest.mark.parametrize("interpolate", [False, True])
+def test_unimodal_branch_vs_reference(channels_last, interpolate):
+    """interpolate=True: setting 0 (maps at half resolution) goes through the fused bilinear
+    interpolation + max-pool kernel (image.py:1278-1283)."""
     from deepviewagg_b200.modules.multimodal.fusion import BimodalFusion
     from deepviewagg_b200.modules.multimodal.modules import UnimodalBranch
     from deepviewagg_b200.modules.multimodal.pooling import BimodalCSRPool, GroupBimodalCSRPool
-    g = load_golden("unimodal_branch_toy")
+    g = load_golden("unimodal_branch_interp" if interpolate else "unimodal_branch_toy")
     mod = _toy_image_data(g, "cuda")
     xs = []
     for im in mod:
@@ -34,7 +37,8 @@ def test_unimodal_branch_vs_reference(channels_last):
         xs.append(x)
     view_pool = GroupBimodalCSRPool(in_map=8, in_mod=16, num_groups=4, use_num=True)
     view_pool.load_state_dict(g["sd"], strict=True)
-    branch = UnimodalBranch(None, BimodalCSRPool(mode="max"), view_pool, BimodalFusion("concatenation")).cuda()
+    branch = UnimodalBranch(None, BimodalCSRPool(mode="max"), view_pool, BimodalFusion("concatenation"),
+                            interpolate=interpolate).cuda()
     branch.train()
     x_3d = g["x_3d"].cuda().requires_grad_(True)
     out = branch({"x_3d": x_3d, "x_seen": None, "modalities": {"image": mod}}, "image")
@@ -86,3 +90,48 @@ def test_containers_on_cuda_match_cpu():
                        canon_pixels(gm["pixels"], gm["atomic_pointers"]))
     assert torch.allclose(mg.features.cpu(), gm["features"], atol=1e-6)
     assert torch.equal(m_cpu.pixels, m.pixels.cpu())
+
+
+@pytest.mark.parametrize("tag", ["half", "quarter"])
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_sparse_interpolation_kernel_bit_exact(tag, channels_last):
+    """dva_interp_pool_fwd/bwd vs the reference's sparse_interpolation executed on CPU: fp32 values
+    bit-identical (same operation order), map gradient within fp32 atomics' reordering; then pooled
+    (max / mean / sum over random pixel segments) against the oracle composition."""
+    import numpy as np
+    from deepviewagg_b200 import ops
+    from oracle.image_oracle import sparse_interpolation_pixels
+    from oracle import scatter_standin as S
+    g = load_golden("sparse_interpolation")
+    W, H, ds = [int(v) for v in g[f"{tag}_size"]]
+    x = g[f"{tag}_x"].cuda()
+    if channels_last:
+        x = x.contiguous(memory_format=torch.channels_last)
+    x.requires_grad_(True)
+    fmap = x.permute(0, 2, 3, 1) if channels_last else x
+    pix, batch = g[f"{tag}_pix"].cuda(), g[f"{tag}_batch"].cuda()
+    for pdt in (torch.int16, torch.int32, torch.int64):
+        out = ops.sparse_interpolation_pixels(fmap, batch, pix.to(pdt), (W, H), channels_last=channels_last)
+        assert torch.equal(out.cpu(), g[f"{tag}_out"]), pdt
+    (gx,) = torch.autograd.grad((out * g[f"{tag}_w"].cuda()).sum(), [x])
+    assert (gx.cpu() - g[f"{tag}_gx"]).abs().max() <= 1e-5 * float(g[f"{tag}_gx"].abs().max())
+    # pooled: pixels sorted by image so that a segment lives in one image, ragged segments with empties
+    order = torch.argsort(batch.cpu(), stable=True)
+    pix_s, batch_s = pix.cpu()[order], batch.cpu()[order]
+    gen = torch.Generator().manual_seed(5)
+    ptr = [0]
+    for b in range(int(batch_s.max()) + 1):
+        lo, hi = int((batch_s < b).sum()), int((batch_s <= b).sum())
+        cuts = torch.sort(torch.randint(lo, hi + 1, (40,), generator=gen)).values.tolist()
+        ptr += cuts + [hi]
+    ptr = torch.tensor(ptr)
+    img = batch_s[torch.clamp(ptr[:-1], max=batch_s.numel() - 1)]
+    vals = torch.from_numpy(sparse_interpolation_pixels(g[f"{tag}_x"].numpy(), pix_s.numpy(), batch_s.numpy(), (W, H)))
+    for reduce in ("max", "min", "sum", "mean"):
+        got = ops.interp_pool(fmap.detach(), img.cuda(), pix_s.int().cuda(), ptr.cuda(), (W, H), reduce=reduce,
+                              channels_last=channels_last)
+        want = S.segment_csr(vals, ptr, reduce=reduce)
+        if reduce in ("max", "min"):
+            assert torch.equal(got.cpu(), want), reduce
+        else:
+            assert (got.cpu() - want).abs().max() <= 1e-5 * max(1.0, float(want.abs().max())), reduce

@@ -120,3 +120,23 @@ def test_simple_pools_and_fusion():
                                g[f"heuristic_{mode}_{feat}"])
     for mode in ("residual", "concatenation", "both", "modality"):
         assert torch.equal(O.bimodal_fusion(g["fusion_a"], g["fusion_b"], mode), g["fusion_" + mode])
+
+
+@pytest.mark.parametrize("tag", ["half", "quarter"])
+def test_sparse_interpolation_restatement_is_bit_exact(tag):
+    """oracle/image_oracle.py vs the reference's sparse_interpolation (image.py:105-170) executed by
+    make_golden; the torch restatement in core/multimodal/image.py (CPU tensors) as well."""
+    import numpy as np
+    from oracle.image_oracle import sparse_interpolation_pixels
+    from deepviewagg_b200.core.multimodal.image import sparse_interpolation
+    g = load_golden("sparse_interpolation")
+    W, H, ds = [int(v) for v in g[f"{tag}_size"]]
+    x, pix, batch = g[f"{tag}_x"], g[f"{tag}_pix"], g[f"{tag}_batch"]
+    out = sparse_interpolation_pixels(x.numpy(), pix.numpy(), batch.numpy(), (W, H))
+    assert np.array_equal(out, g[f"{tag}_out"].numpy())
+    coords = (pix / (torch.tensor([[W, H]], dtype=torch.float) - 1))[:, [1, 0]]
+    xt = x.clone().requires_grad_(True)
+    o2 = sparse_interpolation(xt, coords, batch)
+    assert torch.equal(o2.detach(), g[f"{tag}_out"])
+    (gx,) = torch.autograd.grad((o2 * g[f"{tag}_w"]).sum(), [xt])
+    assert rel_err(gx, g[f"{tag}_gx"]) < 1e-6
