@@ -5,6 +5,11 @@ call, H2D of every input -> fused forward -> fused backward -> D2H of every resu
 CUDA stream through the C ABI.  bench.py times this call for its `e2e` number (host<->device
 copies inside the timed region).  Operator semantics are those of ops.view_attention
 (modules.py:518 + pooling.py:285-300).
+
+`ViewAttentionHostPipeline` keeps `depth` plans on `depth` CUDA streams: consecutive steps go to
+alternating slots, so step k+1's H2D copies run on the copy-in engine while step k computes and
+streams its results out on the copy-out engine (PCIe is full duplex; a single stream uses one
+direction at a time).  Every step still moves all of its inputs and results.
 """
 import torch
 
@@ -88,3 +93,45 @@ class ViewAttentionHostPlan:
             host.copy_(getattr(self, k), non_blocking=True)
             d2h += host.numel() * host.element_size()
         return h2d, d2h
+
+
+class ViewAttentionHostPipeline:
+    """`depth` independent ViewAttentionHostPlan slots, one CUDA stream each.
+
+        pipe = ViewAttentionHostPipeline(2, N, V, R, C, G, ...)
+        for step in steps:
+            ev = pipe.submit(ins[step], outs[step % pipe.depth])   # returns at once
+        pipe.drain()                                               # all results are in `outs`
+
+    Results of a step are valid once its event completed; a slot's `outs` must not be reused
+    by the caller before that.  Slot reuse on the device is ordered by the slot's stream."""
+
+    def __init__(self, depth, *plan_args, first_plan=None, **plan_kwargs):
+        assert depth >= 1
+        self.depth = depth
+        self.plans = [first_plan if (k == 0 and first_plan is not None)
+                      else ViewAttentionHostPlan(*plan_args, **plan_kwargs) for k in range(depth)]
+        dev = self.plans[0].device
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+        self._next = 0
+
+    def submit(self, ins, outs, after_step=None):
+        """Enqueue one full step (H2D, fwd, bwd, D2H) on the next slot; `after_step(plan)` runs on
+        the slot's stream after the kernels (e.g. the gradient all-reduce).  Returns
+        (event, h2d_bytes, d2h_bytes)."""
+        k = self._next
+        self._next = (k + 1) % self.depth
+        plan, stream = self.plans[k], self.streams[k]
+        stream.wait_stream(torch.cuda.current_stream(plan.device))
+        with torch.cuda.stream(stream):
+            h2d, d2h = plan.run_host(ins, outs)
+            if after_step is not None:
+                after_step(plan)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        return ev, h2d, d2h
+
+    def drain(self):
+        cur = torch.cuda.current_stream(self.plans[0].device)
+        for s in self.streams:
+            cur.wait_stream(s)
