@@ -198,6 +198,17 @@ def workload_config(args, world):
             "l2": "inputs (>16 GB per step) exceed the 126 MB L2; no explicit flush needed"}
 
 
+def ncu_traffic(args):
+    """DRAM bytes per launch measured by ncu for this exact workload (profiles/ncu_traffic.json), or {}."""
+    key = (f"points={args.points} views={args.views} channels={args.channels} groups={args.groups} "
+           f"dtype={args.dtype} idx={args.idx} counts={args.counts}")
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(key, {})
+    except (OSError, ValueError):
+        return {}
+
+
 # ---------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
@@ -300,11 +311,14 @@ def main():
     ach_bwd = b_bwd / (bwd_ms * 1e-3) / 1e9
     ach_fwd = b_fwd / (fwd_ms * 1e-3) / 1e9
     ach_step = (b_fwd + b_bwd) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9
+    traffic = ncu_traffic(args)
     roofline = {"bound": "hbm", "kernel": "view_attention_bwd_kernel", "achieved": ach_bwd, "peak": peak,
-                "unit": "GB/s", "frac": ach_bwd / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": ach_bwd / peak, "traffic": traffic.get("view_attention_bwd_kernel"),
+                "traffic_source": traffic.get("source"), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": b_bwd, "ms_per_launch": bwd_ms}
     extra_roof = {
         "fwd": {"kernel": "view_attention_fwd_kernel", "achieved": ach_fwd, "frac": ach_fwd / peak,
+                "traffic": traffic.get("view_attention_fwd_kernel"),
                 "algorithmic_bytes_per_launch": b_fwd, "ms_per_launch": fwd_ms},
         "fwd_plus_bwd": {"achieved": ach_step, "frac": ach_step / peak,
                          "algorithmic_bytes": b_fwd + b_bwd, "ms": fwd_ms + bwd_ms}}
