@@ -50,6 +50,11 @@ SIGNATURES = {
                                    _i64, _i64, _i64, _i64, _i32, _i32, _vp]),
     "dva_interp_pool_bwd": (_i32, [_vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _i64,
                                    _i64, _i64, _i64, _i64, _i32, _i32, _vp]),
+    "dva_knn_cell_ids": (_i32, [_vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _i32, _i32, _vp]),
+    "dva_knn_grid": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _f32, _f32, _i32, _i32, _i32,
+                            _vp, _vp, _vp]),
+    "dva_neighborhood_features": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _f64, _i32, _i32, _vp,
+                                         _i64, _i64, _vp]),
     "dva_linear_gemm_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32, _i32]),
     "dva_linear_gemm": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _sz, _vp]),
     "dva_bn_workspace_bytes": (_sz, [_i64, _i64]),

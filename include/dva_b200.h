@@ -168,6 +168,36 @@ int dva_interp_pool_bwd(const void* grad_out, int channels_last, const int64_t* 
                         void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * N1  neighbourhood-based mapping features (density, occlusion)
+ *   replaces NeighborhoodBasedMappingFeatures._process,
+ *   core/data_transform/multimodal/image.py:483-612 (KeOps argKmin branch :504-514; the FAISS
+ *   branch is approximate and not reproduced).
+ *   dva_knn_cell_ids : cell[i] = linear cell of point i in a gx x gy x gz grid of `cell_size`
+ *                      cubes anchored at (ox,oy,oz) (clamped).  The caller sorts points by cell
+ *                      and builds cell_ptr [gx*gy*gz+1] (dva_csr_pointers_from_sorted).
+ *   dva_knn_grid     : exact k nearest neighbours (self included), k <= 64, of every point among
+ *                      all points; squared distance (dx*dx + dy*dy) + dz*dz in fp32, ties by
+ *                      index.  neighbors [n,k] int64 and dist2 [n,k] (nullable) are indexed by
+ *                      ORIGINAL point id, ascending (dist2, id).
+ *   dva_neighborhood_features : out [V, nk*(density + occlusion)] fp32 = for every k of the
+ *                      ascending klist: density of the view's point ((k+1)/(3.1416 d_k^2)/(1/voxel^2),
+ *                      NaN -> 1, :527-537), then occlusion of the view ((1 + #neighbours seen by
+ *                      the view's image)/(k+1), :563-584).  view_ptr [N+1] / images [V]: the view
+ *                      CSR; view_point [V] = point of each view.
+ * ------------------------------------------------------------------------------------------ */
+int dva_knn_cell_ids(const float* xyz, int64_t* cell, int64_t n, float ox, float oy, float oz,
+                     float cell_size, int gx, int gy, int gz, void* stream);
+int dva_knn_grid(const float* xyz_sorted, const int64_t* cell_sorted, const int64_t* order,
+                 const int64_t* cell_ptr, int64_t n, int k, float ox, float oy, float oz,
+                 float cell_size, int gx, int gy, int gz, int64_t* neighbors, float* dist2,
+                 void* stream);
+int dva_neighborhood_features(const float* xyz, const int64_t* neighbors, int kmax,
+                              const int64_t* view_ptr, const int64_t* images,
+                              const int64_t* view_point, const int32_t* klist, int nk,
+                              double voxel, int density, int occlusion, float* out, int64_t N,
+                              int64_t V, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * P9  dense projection GEMM of an MLP layer (tcgen05 / TMA / TMEM)
  *   replaces the nn.Linear(bias=False) of base_modules.py:42 in every pool MLP.
  *   layout 0: D[M,N] = A[M,K] . B[N,K]^T   (forward,  B = weight [out,in])

@@ -192,6 +192,7 @@ def main():
     make_branch_golden(ref)
     make_branch_golden(ref, interpolate=True, name="unimodal_branch_interp")
     make_interp_golden(ref)
+    make_neighborhood_golden(ref)
     make_camera_golden(ref)
 
 
@@ -336,6 +337,44 @@ def make_interp_golden(ref):
         arrays.update({f"{tag}_pix": pix, f"{tag}_batch": batch, f"{tag}_x": x, f"{tag}_out": out,
                        f"{tag}_w": w, f"{tag}_gx": gx, f"{tag}_size": np.array([W, H, ds])})
     save("sparse_interpolation", **arrays)
+
+
+def make_neighborhood_golden(ref):
+    """NeighborhoodBasedMappingFeatures (core/data_transform/multimodal/image.py:431-612) run by
+    the reference on a noisy two-plane cloud; the KeOps argKmin is the dense stand-in of
+    oracle/ref_loader.py (exact search, ties by index).  Cases: k list with existing features,
+    single k without features, density only / occlusion only."""
+    import numpy as np
+    T = ref_loader.load_transforms()
+    I = ref.image
+    gen = torch.Generator().manual_seed(99)
+    N, n_img = 2500, 6
+    uv = torch.rand(N, 2, generator=gen) * torch.tensor([8.0, 5.0])
+    z = torch.where(torch.rand(N, generator=gen) < 0.7, 0.02 * torch.randn(N, generator=gen),
+                    1.5 + 0.02 * torch.randn(N, generator=gen))
+    pos = torch.cat([uv, z[:, None]], 1)
+    pos[10] = pos[11]                                       # exact duplicates: zero distance, index ties
+    pos[12] = pos[11]
+    (st,) = toy_settings(gen, N, [(64, 48, n_img, 2.5)])
+    arrays = dict(pos=pos, pid=st["pid"], iid=st["iid"], pix=st["pix"], feat=st["feat"],
+                  size=np.array([64, 48, n_img]))
+
+    def run(tag, with_feat, **kw):
+        im = I.SameSettingImageData(path=np.array([f"img_{i}" for i in range(n_img)]), pos=torch.zeros(n_img, 3),
+                                    opk=torch.zeros(n_img, 3), ref_size=(64, 48), proj_upscale=1, downscale=1)
+        im.mappings = I.ImageMapping.from_dense(st["pid"], st["iid"], st["pix"], st["feat"] if with_feat else None,
+                                                num_points=N)
+        tr = T.NeighborhoodBasedMappingFeatures(use_cuda=False, use_faiss=False, **kw)
+        _, out = tr(ref_loader.load_reference().Data(pos=pos), im)
+        arrays[f"{tag}_features"] = out.mappings.features
+
+    run("klist", True, k=[20, 5], voxel=0.05)
+    run("k7", False, k=7)
+    run("density_only", False, k=[4, 16], voxel=0.1, occlusion=False)
+    run("occlusion_only", True, k=10, density=False)
+    d = ((pos[:, None, :] - pos[None, :, :]) ** 2).sum(dim=2)
+    arrays["neighbors_k20"] = torch.sort(d, dim=1, stable=True).indices[:, :20]
+    save("neighborhood_features", **arrays)
 
 
 def make_integer_golden(ref):

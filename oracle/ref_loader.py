@@ -106,3 +106,62 @@ def load_reference(with_visibility=True):
                        "torch_points3d/modules/multimodal/modules.py")
     _loaded = ns
     return ns
+
+
+class DenseLazyTensor:
+    """Dense stand-in for the subset of pykeops.torch.LazyTensor that
+    NeighborhoodBasedMappingFeatures uses (core/data_transform/multimodal/image.py:504-514):
+    broadcasting `-`, `** 2`, `.sum(dim=2)` and `.argKmin(K, dim=1)`.  KeOps documents argKmin as
+    the indices of the K smallest values along `dim`; the dense emulation takes them from a stable
+    sort, i.e. ties (and only ties) are ordered by index.  Small N only (N x N x 3 floats)."""
+
+    def __init__(self, t):
+        self.t = t
+
+    def __sub__(self, other):
+        return DenseLazyTensor(self.t - other.t)
+
+    def __pow__(self, p):
+        return DenseLazyTensor(self.t ** p)
+
+    def sum(self, dim):
+        return DenseLazyTensor(self.t.sum(dim=dim))
+
+    def argKmin(self, K, dim):
+        import torch
+        return torch.sort(self.t, dim=dim, stable=True).indices[:, :K]
+
+
+def load_transforms():
+    """The reference's image transforms module (core/data_transform/multimodal/image.py), with
+    stand-ins for what it imports but the neighbourhood-feature path never touches:
+    torch_geometric `Data` (attribute bag with `num_nodes`), the 3D samplers, FAISS finder."""
+    ns = load_reference()
+    if hasattr(ns, "transforms"):
+        return ns.transforms
+    tg = _stub("torch_geometric")
+    tgd = _stub("torch_geometric.data")
+
+    class Data:
+        def __init__(self, **kw):
+            self.__dict__.update(kw)
+
+        @property
+        def num_nodes(self):
+            return self.pos.shape[0]
+
+    tgd.Data = Data
+    tg.data = tgd
+    dt = _stub("torch_points3d.core.data_transform")
+    for name in ("SphereSampling", "CylinderSampling", "GridSampling3D", "SaveOriginalPosId"):
+        setattr(dt, name, type(name, (), {}))
+    so = _stub("torch_points3d.core.spatial_ops")
+    nf = _stub("torch_points3d.core.spatial_ops.neighbour_finder")
+    nf.FAISSGPUKNNNeighbourFinder = type("FAISSGPUKNNNeighbourFinder", (), {})
+    so.neighbour_finder = nf
+    sys.modules["pykeops.torch"].LazyTensor = DenseLazyTensor
+    _stub("torch_points3d.core.data_transform.multimodal")
+    ns.transforms = _load("torch_points3d.core.data_transform.multimodal.image",
+                          "torch_points3d/core/data_transform/multimodal/image.py")
+    ns.Data = Data
+    return ns.transforms

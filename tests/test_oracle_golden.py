@@ -140,3 +140,31 @@ def test_sparse_interpolation_restatement_is_bit_exact(tag):
     assert torch.equal(o2.detach(), g[f"{tag}_out"])
     (gx,) = torch.autograd.grad((o2 * g[f"{tag}_w"]).sum(), [xt])
     assert rel_err(gx, g[f"{tag}_gx"]) < 1e-6
+
+
+def test_neighborhood_features_restatement():
+    """oracle/neighborhood_oracle.py vs the reference's NeighborhoodBasedMappingFeatures executed by
+    make_golden (image.py:483-612): neighbours identical, occlusion bit-exact, density within one
+    ulp of the scalar division (the reference divides by a Python scalar)."""
+    import numpy as np
+    from oracle.neighborhood_oracle import knn_bruteforce, neighborhood_features
+    from deepviewagg_b200.core.multimodal.image import ImageMapping
+    g = load_golden("neighborhood_features")
+    pos = g["pos"].numpy()
+    nbr, d2 = knn_bruteforce(pos, 20)
+    assert np.array_equal(nbr, g["neighbors_k20"].numpy())
+    assert (d2[:, 1:] >= d2[:, :-1]).all() and (d2[[10, 11, 12], :3] == 0).all()      # the duplicated point
+    m = ImageMapping.from_dense(g["pid"], g["iid"], g["pix"], g["feat"], num_points=len(pos))
+    cases = (("klist", dict(k_list=[20, 5], voxel=0.05), 8), ("k7", dict(k_list=[7]), 0),
+             ("density_only", dict(k_list=[4, 16], voxel=0.1, occlusion=False), 0),
+             ("occlusion_only", dict(k_list=[10], density=False), 8))
+    for tag, kw, n_old in cases:
+        got = neighborhood_features(pos, nbr, m.pointers.numpy(), m.images.numpy(), **kw)
+        want = g[f"{tag}_features"].numpy()
+        if n_old:                                                   # existing columns are kept in front
+            assert np.array_equal(want[:, :n_old], m.features.numpy()), tag
+        want = want[:, n_old:]
+        assert got.shape == want.shape, tag
+        fin = np.isfinite(want)
+        assert (np.isfinite(got) == fin).all(), tag
+        assert np.abs(got[fin] - want[fin]).max() <= 2e-7 * np.abs(want[fin]).max(), tag
