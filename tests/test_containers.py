@@ -141,3 +141,31 @@ def test_image_data_view_indexing_matches_reference():
     # selecting points drops unseen images and renumbers the rest
     sub = mod.select_points(torch.arange(0, 50), mode="pick")
     assert sub.num_points == 50 and all(int(im.mappings.images.max()) < im.num_views for im in sub)
+
+
+def test_flat_mapping_file_round_trip(tmp_path):
+    """the flat on-disk mapping format reloads to identical tensors (memmap
+    read, no pickling) and keeps the container behaviour (view sorting, point selection)."""
+    from deepviewagg_b200.core.multimodal.storage import load_image_data, read_header, save_image_data
+    g = load_golden("unimodal_branch_toy")
+    mod = _toy_image_data(g)
+    mod[0].extras["extrinsic"] = torch.arange(mod[0].num_views * 16, dtype=torch.float64).view(-1, 4, 4)
+    path = save_image_data(str(tmp_path / "scene.dvamap"), mod)
+    meta, base = read_header(path)
+    assert base % 64 == 0 and all(e["offset"] % 64 == 0 for e in meta["arrays"].values())
+    back = load_image_data(path)
+    assert len(back) == len(mod)
+    for a, b in zip(mod, back):
+        assert torch.equal(a.mappings.pointers, b.mappings.pointers)
+        assert torch.equal(a.mappings.images, b.mappings.images)
+        assert torch.equal(a.mappings.values[1].pointers, b.mappings.values[1].pointers)
+        assert torch.equal(a.mappings.pixels, b.mappings.pixels) and a.mappings.pixels.dtype == b.mappings.pixels.dtype
+        assert torch.equal(a.mappings.features, b.mappings.features)
+        assert a.ref_size == b.ref_size and a.downscale == b.downscale and a.num_views == b.num_views
+        assert torch.equal(a.pos, b.pos)
+    assert torch.equal(back[0].extras["extrinsic"], mod[0].extras["extrinsic"])
+    assert torch.equal(back.view_cat_csr_indexing, mod.view_cat_csr_indexing)
+    idx = torch.arange(0, mod.num_points, 3)
+    sa, sb = mod.select_points(idx), back.select_points(idx)
+    assert torch.equal(sa[0].mappings.pointers, sb[0].mappings.pointers)
+    assert torch.equal(sa[1].mappings.images, sb[1].mappings.images)

@@ -135,3 +135,20 @@ def test_sparse_interpolation_kernel_bit_exact(tag, channels_last):
             assert torch.equal(got.cpu(), want), reduce
         else:
             assert (got.cpu() - want).abs().max() <= 1e-5 * max(1.0, float(want.abs().max())), reduce
+
+
+def test_flat_mapping_file_uploads_to_cuda(tmp_path):
+    """storage.load_image_data(device='cuda'): memmap -> pinned staging -> async H2D, tensors equal
+    the originals and the loaded ImageData drives the fused branch kernels."""
+    from deepviewagg_b200.core.multimodal.storage import load_image_data, save_image_data
+    g = load_golden("unimodal_branch_toy")
+    mod = _toy_image_data(g)
+    path = save_image_data(str(tmp_path / "scene.dvamap"), mod)
+    back = load_image_data(path, device="cuda")
+    torch.cuda.synchronize()
+    for a, b in zip(mod, back):
+        assert b.mappings.pointers.is_cuda and b.mappings.pixels.is_cuda
+        assert torch.equal(a.mappings.pointers, b.mappings.pointers.cpu())
+        assert torch.equal(a.mappings.pixels, b.mappings.pixels.cpu())
+        assert torch.equal(a.mappings.features, b.mappings.features.cpu())
+    assert torch.equal(back.view_cat_csr_indexing.cpu(), mod.view_cat_csr_indexing)
