@@ -34,6 +34,7 @@ SIGNATURES = {
     "dva_segment_softmax_csr_bwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp]),
     "dva_view_attention_fwd": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                       _i64, _i64, _i64, _i64, _i64, _i32, _f32, _i32, _vp]),
+    "dva_view_attention_set_path": (_i32, [_i32]),
     "dva_view_attention_bwd_workspace_bytes": (_sz, [_i64]),
     "dva_view_attention_bwd": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                       _vp, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _i32, _i32,

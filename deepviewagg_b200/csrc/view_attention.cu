@@ -20,23 +20,10 @@
 // HBM bytes per launch (s = sizeof(T)):
 //   fwd: V*(C*s + 4 + 4G) + N*(8 + C*s) (+ N*12G saved statistics when training)
 //   bwd: V*(2*C*s + 4 + 8G) + N*(8 + C*s + 12G)
-#include "dva_common.cuh"
+#include "view_attention.cuh"
+#include <stdlib.h>
 
 namespace dva {
-
-struct VAParams {
-  const void* x; const void* idx; int idx64;
-  const float* compat; const int64_t* ptr;
-  const float* gate_w; const float* gate_b;
-  // fwd
-  void* out; float* att; float* seg_max; float* seg_den; int32_t* seg_arg;
-  // bwd
-  const void* gout; const float* s_max; const float* s_den; const int32_t* s_arg;
-  void* gx; float* gcompat; float* gate_partial; int scatter;
-  int64_t N, V, R;
-  int C, G, group_scaling;
-  float eps;
-};
 
 #ifndef DVA_FWD_UNROLL
 #define DVA_FWD_UNROLL 8
@@ -53,7 +40,6 @@ struct VAParams {
 constexpr int kWarps = 8;          // warps per CTA
 constexpr int kUnroll = DVA_FWD_UNROLL;     // fwd: row loads in flight per lane (x CPL)
 constexpr int kUnrollBwd = DVA_BWD_UNROLL;  // bwd: row loads in flight per lane (x CPL)
-constexpr int kTileStride = 33;    // att tile is [G][33]: (g,v) -> bank (g+v)%32, conflict-free
 
 // A row chunk in flight: the raw 16 bytes (or one scalar) -- unpacked to fp32 only at use so
 // that kUnroll loads cost 4 registers each whatever the storage type.
@@ -88,12 +74,6 @@ __device__ __forceinline__ const char* row_addr(const char* base, uint32_t row, 
 }
 __device__ __forceinline__ char* row_addr(char* base, uint32_t row, uint32_t row_bytes) {
   return base + (uint64_t)row * row_bytes;
-}
-
-// reduce over the lanes that share (lane % G): offsets 16 .. G
-__device__ __forceinline__ float group_lane_sum(float v, int G) {
-  for (int off = 16; off >= G; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-  return v;
 }
 
 // Per-point softmax statistics over the flat (view, group) scores of one segment.
@@ -703,6 +683,34 @@ template <typename T> static int bwd_typed(const VAParams& P, int* grid, cudaStr
 
 static bool pow2_le32(int64_t g) { return g >= 1 && g <= 32 && (g & (g - 1)) == 0; }
 
+// 0 = auto, 1 = streaming kernels, 2 = ring kernels (when applicable).  Process-wide tuning knob
+// (dva_view_attention_set_path / DVA_VA_PATH=auto|stream|ring, read once); results do not depend on it.
+static std::atomic<int>& va_path() {
+  static std::atomic<int> p{[] {
+    const char* e = getenv("DVA_VA_PATH");
+    if (e == nullptr) return 0;
+    if (strcmp(e, "stream") == 0) return 1;
+    if (strcmp(e, "ring") == 0) return 2;
+    return 0;
+  }()};
+  return p;
+}
+
+// auto: the ring kernels win wherever the per-point dependent-load chain of the streaming kernels
+// is exposed -- rows under 512 bytes, or fewer than kRingMaxMeanViews views per point on average.
+#ifndef DVA_RING_MAX_MEAN_VIEWS
+#define DVA_RING_MAX_MEAN_VIEWS 24
+#endif
+static bool use_ring(const VAParams& P, int dtype, bool applicable) {
+  if (!applicable) return false;
+  const int path = va_path().load(std::memory_order_relaxed);
+  if (path == 1) return false;
+  if (path == 2) return true;
+  const size_t esz = dtype == DVA_F32 ? 4 : 2;
+  if ((size_t)P.C * esz < 512) return true;
+  return P.V < (int64_t)DVA_RING_MAX_MEAN_VIEWS * P.N;
+}
+
 }  // namespace dva
 
 using namespace dva;
@@ -730,12 +738,20 @@ extern "C" int dva_view_attention_fwd(const void* x, const void* idx, int idx_is
   P.seg_max = seg_max; P.seg_den = seg_den; P.seg_arg = seg_arg;
   P.N = N; P.V = V; P.R = R; P.C = (int)C; P.G = (int)G; P.group_scaling = group_scaling; P.eps = eps;
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype != DVA_F32 && dtype != DVA_BF16 && dtype != DVA_F16) return fail(DVA_EINVAL, "view_attention_fwd: unknown dtype");
+  if (use_ring(P, dtype, va_ring_fwd_applicable(P, dtype))) return va_ring_fwd(P, dtype, st);
   switch (dtype) {
     case DVA_F32: return fwd_typed<float>(P, st);
     case DVA_BF16: return fwd_typed<__nv_bfloat16>(P, st);
     case DVA_F16: return fwd_typed<__half>(P, st);
     default: return fail(DVA_EINVAL, "view_attention_fwd: unknown dtype");
   }
+}
+
+extern "C" int dva_view_attention_set_path(int path) {
+  if (path < 0 || path > 2) return fail(DVA_EINVAL, "view_attention_set_path: 0 = auto, 1 = streaming, 2 = ring");
+  va_path().store(path, std::memory_order_relaxed);
+  return DVA_OK;
 }
 
 extern "C" size_t dva_view_attention_bwd_workspace_bytes(int64_t G) {
@@ -776,11 +792,15 @@ extern "C" int dva_view_attention_bwd(const void* x, const void* idx, int idx_is
   P.N = N; P.V = V; P.R = R; P.C = (int)C; P.G = (int)G; P.group_scaling = group_scaling;
   int grid = 1;
   int rc;
-  switch (dtype) {
-    case DVA_F32: rc = bwd_typed<float>(P, &grid, st); break;
-    case DVA_BF16: rc = bwd_typed<__nv_bfloat16>(P, &grid, st); break;
-    case DVA_F16: rc = bwd_typed<__half>(P, &grid, st); break;
-    default: return fail(DVA_EINVAL, "view_attention_bwd: unknown dtype");
+  if (dtype != DVA_F32 && dtype != DVA_BF16 && dtype != DVA_F16) return fail(DVA_EINVAL, "view_attention_bwd: unknown dtype");
+  if (use_ring(P, dtype, va_ring_bwd_applicable(P, dtype))) {
+    rc = va_ring_bwd(P, dtype, &grid, st);
+  } else {
+    switch (dtype) {
+      case DVA_F32: rc = bwd_typed<float>(P, &grid, st); break;
+      case DVA_BF16: rc = bwd_typed<__nv_bfloat16>(P, &grid, st); break;
+      default: rc = bwd_typed<__half>(P, &grid, st); break;
+    }
   }
   if (rc) return rc;
   if (gating) {

@@ -100,6 +100,13 @@ int dva_view_attention_fwd(const void* x, const void* idx, int idx_is_i64, const
                            int32_t* seg_arg, int64_t N, int64_t V, int64_t R, int64_t C,
                            int64_t G, int group_scaling, float eps, int dtype, void* stream);
 
+/* Implementation choice of the fused pair (tuning / test knob, process-wide; results are the same
+ * up to fp32 summation order): 0 = auto (default; also DVA_VA_PATH=auto|stream|ring in the
+ * environment), 1 = streaming kernels (rows in registers, one point per warp at a time),
+ * 2 = ring kernels (rows staged in shared memory by async copies across point boundaries; used
+ * when rows are <= 512 bytes of whole 16-byte chunks, else the streaming kernels run). */
+int dva_view_attention_set_path(int path);
+
 /* Backward of the chain above.
  *   grad_out [N,C] (dtype) -> grad_x_rows [V,C] (dtype; row v is d/d(x[idx[v]]); when
  *   scatter_rows!=0 and idx!=null it is written to row idx[v] of a [R,C] buffer instead, which

@@ -95,6 +95,17 @@ def test_segment_edge_cases():
         ops.segment_csr(big, torch.tensor([0, 100000], dtype=torch.int32).cuda())
 
 
+@pytest.fixture(params=["stream", "ring"])
+def va_path(request):
+    """Run the test once per implementation of the fused pair (streaming kernels / ring kernels,
+    dva_view_attention_set_path); the default 'auto' choice is restored afterwards."""
+    from deepviewagg_b200 import _lib
+    lib = _lib.load()
+    assert lib.dva_view_attention_set_path({"stream": 1, "ring": 2}[request.param]) == 0
+    yield request.param
+    assert lib.dva_view_attention_set_path(0) == 0
+
+
 # ------------------------------------------------------------------------------------------------
 # the fused kernel vs the oracle
 # ------------------------------------------------------------------------------------------------
@@ -151,35 +162,46 @@ def _run_va(N, mean_v, C, G, seed, dtype=torch.float32, use_idx=None, gating=Tru
 
 @pytest.mark.parametrize("C,G", [(128, 4), (64, 4), (32, 4), (16, 2), (512, 4), (256, 8), (8, 8),
                                  (10, 4), (20, 1), (96, 32), (1024, 4), (7, 1), (130, 2), (36, 4)])
-def test_view_attention_shapes(C, G):
+def test_view_attention_shapes(C, G, va_path):
     _run_va(300, 6, C, G, seed=C * 7 + G)
 
 
 @pytest.mark.parametrize("kw", [dict(gating=False), dict(scaling=False), dict(use_idx=torch.int32),
                                 dict(use_idx=torch.int64), dict(use_idx=torch.int64, perm=False),
                                 dict(gating=False, scaling=False, use_idx=torch.int32)])
-def test_view_attention_variants(kw):
+def test_view_attention_variants(kw, va_path):
     _run_va(257, 5, 128, 4, seed=5, **kw)
     _run_va(120, 9, 48, 4, seed=6, **kw)
 
 
-def test_view_attention_long_segments_and_empties():
+def test_view_attention_long_segments_and_empties(va_path):
     _run_va(40, 90, 128, 4, seed=1)                 # segments > 32 views (multi-chunk path)
     _run_va(9, 300, 64, 4, seed=2, use_idx=torch.int32)
     _run_va(64, 3, 128, 4, seed=3, p_empty=0.9)     # mostly unseen points
     _run_va(50, 4, 128, 4, seed=4, p_empty=1.0)     # no view at all (V == 0)
     _run_va(1, 1, 128, 4, seed=8, p_empty=0.0)
+    # ring kernels: segments cut into several pieces at arbitrary batch offsets, 16/32-row batches
+    _run_va(40, 90, 64, 4, seed=13)
+    _run_va(700, 21, 32, 4, seed=14, use_idx=torch.int32)
+    _run_va(500, 40, 128, 8, seed=15, dtype=torch.float32)
+    _run_va(33, 70, 16, 4, seed=16)
+
+
+def test_view_attention_many_ranges(va_path):
+    # more point ranges than resident warps: every warp walks several ranges (ring refill between them)
+    _run_va(60000, 3, 64, 4, seed=21, use_idx=torch.int32)
+    _run_va(45000, 2, 128, 4, seed=22, p_empty=0.5)
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 1.6e-2), (torch.float16, 2e-3)])
-def test_view_attention_half_storage(dtype, tol):
+def test_view_attention_half_storage(dtype, tol, va_path):
     # storage-precision parity (fp32 accumulate): reported separately from the 1e-4 fp32 bar
     _run_va(300, 8, 128, 4, seed=10, dtype=dtype, tol=tol)
     _run_va(200, 8, 64, 4, seed=11, dtype=dtype, tol=tol, use_idx=torch.int32)
     _run_va(100, 8, 12, 4, seed=12, dtype=dtype, tol=tol)   # non-vectorisable C
 
 
-def test_view_attention_zero_points():
+def test_view_attention_zero_points(va_path):
     from deepviewagg_b200 import ops
     out, att, _ = ops.view_attention(torch.zeros(0, 16).cuda(), torch.zeros(0, 4).cuda(),
                                      torch.zeros(1, dtype=torch.long).cuda(), 4)
@@ -243,7 +265,7 @@ def _module_from_fixture(g, cls):
 
 @pytest.mark.parametrize("name", ["group_pool_toy", "group_pool_c64", "group_pool_usemod",
                                   "group_pool_g1_nogate", "group_pool_oddgroups", "group_pool_minmax"])
-def test_group_pool_module_vs_reference(name):
+def test_group_pool_module_vs_reference(name, va_path):
     from deepviewagg_b200.modules.multimodal.pooling import GroupBimodalCSRPool
     g = load_golden(name)
     m, kw = _module_from_fixture(g, GroupBimodalCSRPool)
@@ -275,7 +297,7 @@ def test_group_pool_module_vs_reference(name):
 
 
 @pytest.mark.parametrize("name", ["qkv_pool_base", "qkv_pool_modqk"])
-def test_qkv_pool_module_vs_reference(name):
+def test_qkv_pool_module_vs_reference(name, va_path):
     from deepviewagg_b200.modules.multimodal.pooling import QKVBimodalCSRPool
     g = load_golden(name)
     m, kw = _module_from_fixture(g, QKVBimodalCSRPool)
@@ -313,7 +335,7 @@ def test_simple_pools_and_fusion_modules():
     assert BimodalFusion("residual")(None, b) is b and BimodalFusion("residual")(a, None) is a
 
 
-def test_row_index_fusion_equals_materialised_gather():
+def test_row_index_fusion_equals_materialised_gather(va_path):
     """GroupBimodalCSRPool(row_index=perm) == GroupBimodalCSRPool on x_mod[perm] (modules.py:518)."""
     from deepviewagg_b200.modules.multimodal.pooling import GroupBimodalCSRPool
     g = load_golden("group_pool_c64")
@@ -332,7 +354,7 @@ def test_row_index_fusion_equals_materialised_gather():
 # ------------------------------------------------------------------------------------------------
 # BASELINE-size properties (no oracle can run at 1M x 32 x 128 in seconds)
 # ------------------------------------------------------------------------------------------------
-def test_full_size_properties():
+def test_full_size_properties(va_path):
     from deepviewagg_b200 import ops
     N, v, C, G = 1_000_000, 32, 128, 4
     V = N * v
