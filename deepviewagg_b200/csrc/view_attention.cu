@@ -696,19 +696,21 @@ static std::atomic<int>& va_path() {
   return p;
 }
 
-// auto: the ring kernels win wherever the per-point dependent-load chain of the streaming kernels
-// is exposed -- rows under 512 bytes, or fewer than kRingMaxMeanViews views per point on average.
+// auto (measured on B200, tools/bench_shapes.py, profiles/r1_shapes_*.json): the ring kernels win
+// where per-point scalar work dominates -- short segments.  Forward: fewer than
+// DVA_RING_MAX_MEAN_VIEWS views per point on average; backward: additionally rows of at most 128
+// bytes (with wider rows the streaming backward is as fast and needs no shared-memory tiles).
 #ifndef DVA_RING_MAX_MEAN_VIEWS
-#define DVA_RING_MAX_MEAN_VIEWS 24
+#define DVA_RING_MAX_MEAN_VIEWS 12
 #endif
-static bool use_ring(const VAParams& P, int dtype, bool applicable) {
+static bool use_ring(const VAParams& P, int dtype, bool applicable, bool backward) {
   if (!applicable) return false;
   const int path = va_path().load(std::memory_order_relaxed);
   if (path == 1) return false;
   if (path == 2) return true;
+  if (P.V > (int64_t)DVA_RING_MAX_MEAN_VIEWS * P.N) return false;
   const size_t esz = dtype == DVA_F32 ? 4 : 2;
-  if ((size_t)P.C * esz < 512) return true;
-  return P.V < (int64_t)DVA_RING_MAX_MEAN_VIEWS * P.N;
+  return !backward || (size_t)P.C * esz <= 128;
 }
 
 }  // namespace dva
@@ -739,7 +741,7 @@ extern "C" int dva_view_attention_fwd(const void* x, const void* idx, int idx_is
   P.N = N; P.V = V; P.R = R; P.C = (int)C; P.G = (int)G; P.group_scaling = group_scaling; P.eps = eps;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype != DVA_F32 && dtype != DVA_BF16 && dtype != DVA_F16) return fail(DVA_EINVAL, "view_attention_fwd: unknown dtype");
-  if (use_ring(P, dtype, va_ring_fwd_applicable(P, dtype))) return va_ring_fwd(P, dtype, st);
+  if (use_ring(P, dtype, va_ring_fwd_applicable(P, dtype), false)) return va_ring_fwd(P, dtype, st);
   switch (dtype) {
     case DVA_F32: return fwd_typed<float>(P, st);
     case DVA_BF16: return fwd_typed<__nv_bfloat16>(P, st);
@@ -793,7 +795,7 @@ extern "C" int dva_view_attention_bwd(const void* x, const void* idx, int idx_is
   int grid = 1;
   int rc;
   if (dtype != DVA_F32 && dtype != DVA_BF16 && dtype != DVA_F16) return fail(DVA_EINVAL, "view_attention_bwd: unknown dtype");
-  if (use_ring(P, dtype, va_ring_bwd_applicable(P, dtype))) {
+  if (use_ring(P, dtype, va_ring_bwd_applicable(P, dtype), true)) {
     rc = va_ring_bwd(P, dtype, &grid, st);
   } else {
     switch (dtype) {

@@ -103,8 +103,9 @@ int dva_view_attention_fwd(const void* x, const void* idx, int idx_is_i64, const
 /* Implementation choice of the fused pair (tuning / test knob, process-wide; results are the same
  * up to fp32 summation order): 0 = auto (default; also DVA_VA_PATH=auto|stream|ring in the
  * environment), 1 = streaming kernels (rows in registers, one point per warp at a time),
- * 2 = ring kernels (rows staged in shared memory by async copies across point boundaries; used
- * when rows are <= 512 bytes of whole 16-byte chunks, else the streaming kernels run). */
+ * 2 = ring kernels (rows staged in shared memory by async copies across point boundaries, softmax
+ * statistics one lane per point; need G == 4 and rows of whole 16-byte chunks, <= 512 bytes --
+ * anything else runs on the streaming kernels whatever the setting). */
 int dva_view_attention_set_path(int path);
 
 /* Backward of the chain above.

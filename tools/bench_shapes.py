@@ -36,6 +36,8 @@ SHAPES = [
     ("pyramid_160k_v8_c32", 160_000, 8, 32, "f32", "ragged", "randperm"),
     ("early_160k_v8_c512", 160_000, 8, 512, "f32", "ragged", "randperm"),
     ("sphere_40k_v8_c64", 40_000, 8, 64, "f32", "ragged", "randperm"),
+    ("big_1m_v8_c64", 1_000_000, 8, 64, "f32", "ragged", "randperm"),
+    ("big_1m_v8_c64_bf16", 1_000_000, 8, 64, "bf16", "ragged", "randperm"),
 ]
 
 
