@@ -80,7 +80,9 @@ gather_pool_fwd_kernel(const T* __restrict__ fmap, const int64_t* __restrict__ i
     }
     if (RED == DVA_MEAN) acc /= (float)((p1 - p0) > 0 ? (p1 - p0) : 1);
     out[t] = Cvt<T>::from_f(acc);
-    if ((RED == DVA_MAX || RED == DVA_MIN) && arg != nullptr) arg[t] = best;
+    // the arg table is only needed (and only written) for views with two or more pixels; a
+    // one-pixel view (every view under exact splatting) routes its gradient to that pixel
+    if ((RED == DVA_MAX || RED == DVA_MIN) && arg != nullptr && p1 - p0 >= 2) arg[t] = best;
   }
 }
 
@@ -116,11 +118,215 @@ gather_pool_bwd_kernel(const T* __restrict__ gout, const int64_t* __restrict__ i
     float g = Cvt<T>::to_f(gout[t]);
     if (RED == DVA_MEAN) g /= (float)(p1 - p0);
     if (RED == DVA_MAX || RED == DVA_MIN) {
-      scatter_pixel<CL, INTERP>(gfmap, pix, arg[t], b, c, C, H, W, mw1, mh1, g);
+      scatter_pixel<CL, INTERP>(gfmap, pix, (p1 - p0 == 1) ? p0 : arg[t], b, c, C, H, W, mw1, mh1, g);
     } else {
       for (int64_t p = p0; p < p1; ++p) scatter_pixel<CL, INTERP>(gfmap, pix, p, b, c, C, H, W, mw1, mh1, g);
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// channels-last vector path: LPR lanes own the 16-byte chunks of one view's output row, a warp
+// works on 32/LPR views per step and kGpUnroll steps at once (their index loads, pixel loads and
+// row-chunk loads are issued back to back), so a pixel costs one LDG.128 per lane instead of
+// VEC scalar loads plus 64-bit index arithmetic per channel.  Same arithmetic as the scalar kernel
+// (the bilinear branch keeps the reference's fp32 operation order).
+// ---------------------------------------------------------------------------------------------
+constexpr int kGpWarps = 8;
+
+template <typename T, typename PIX, bool INTERP> struct PixLoad {
+  static constexpr int VEC = Vec16<T>::N;
+  uint4 raw[INTERP ? 4 : 1];
+  Bilin q;
+  // fb: map of the view's image + this lane's chunk offset (bytes); pixel_bytes = C * sizeof(T)
+  __device__ __forceinline__ void issue(const char* __restrict__ fb, const PIX* __restrict__ pix, int64_t p,
+                                        int H, int W, uint32_t pixel_bytes, float mw1, float mh1) {
+    const int px = (int)pix[2 * p], py = (int)pix[2 * p + 1];
+    if constexpr (INTERP) {
+      q = bilin_setup(px, py, H, W, mw1, mh1);
+      raw[0] = ldg_stream16(fb + ((int64_t)q.r0 * W + q.c0) * pixel_bytes);
+      raw[1] = ldg_stream16(fb + ((int64_t)q.r0 * W + q.c1) * pixel_bytes);
+      raw[2] = ldg_stream16(fb + ((int64_t)q.r1 * W + q.c0) * pixel_bytes);
+      raw[3] = ldg_stream16(fb + ((int64_t)q.r1 * W + q.c1) * pixel_bytes);
+    } else {
+      raw[0] = ldg_stream16(fb + ((int64_t)py * W + px) * pixel_bytes);
+    }
+  }
+  __device__ __forceinline__ void value(float (&v)[VEC]) const {
+    if constexpr (INTERP) {
+      float f00[VEC], f01[VEC], f10[VEC], f11[VEC];
+      unpack16<T, VEC>(raw[0], f00); unpack16<T, VEC>(raw[1], f01);
+      unpack16<T, VEC>(raw[2], f10); unpack16<T, VEC>(raw[3], f11);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j)   // image.py:165-168: four products summed left to right
+        v[j] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(q.w00, f00[j]), __fmul_rn(q.w01, f01[j])),
+                                   __fmul_rn(q.w10, f10[j])), __fmul_rn(q.w11, f11[j]));
+    } else {
+      unpack16<T, VEC>(raw[0], v);
+    }
+  }
+};
+
+template <typename T, typename PIX, int LPR, int RED, bool INTERP>
+__global__ void __launch_bounds__(kGpWarps * 32)
+gather_pool_fwd_cl_kernel(const T* __restrict__ fmap, const int64_t* __restrict__ img,
+                          const PIX* __restrict__ pix, const int64_t* __restrict__ aptr,
+                          T* __restrict__ out, int64_t* __restrict__ arg, int C, int H, int W,
+                          int64_t Vw, int64_t P, float mw1, float mh1) {
+  constexpr int VEC = Vec16<T>::N, RPI = 32 / LPR, U = INTERP ? 2 : 4;
+  const int lane = threadIdx.x & 31, sg = lane / LPR, lir = lane % LPR;
+  const int cv = C / VEC, tiles = (cv + LPR - 1) / LPR;
+  const int64_t items = Vw * tiles;
+  const uint32_t pixel_bytes = (uint32_t)C * sizeof(T);
+  const int64_t map_bytes = (int64_t)H * W * pixel_bytes;
+  const char* __restrict__ fbase = reinterpret_cast<const char*>(fmap);
+  const int64_t gwarp = (int64_t)blockIdx.x * kGpWarps + (threadIdx.x >> 5);
+  const int64_t stride = (int64_t)gridDim.x * kGpWarps * RPI * U;
+  for (int64_t it0 = gwarp * RPI * U; it0 < items; it0 += stride) {
+    int64_t w[U], p0[U]; int n[U], ck[U]; bool act[U];
+    const char* fb[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t item = it0 + u * RPI + sg;
+      act[u] = item < items;
+      w[u] = act[u] ? (tiles == 1 ? item : item / tiles) : 0;
+      ck[u] = (int)(item - w[u] * tiles) * LPR + lir;
+      act[u] = act[u] && ck[u] < cv;
+      p0[u] = aptr[w[u]];
+      n[u] = (int)(aptr[w[u] + 1] - p0[u]);
+      fb[u] = fbase + img[w[u]] * map_bytes + (act[u] ? ck[u] * 16 : 0);
+    }
+    PixLoad<T, PIX, INTERP> pl[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (n[u] > 0) pl[u].issue(fb[u], pix, p0[u], H, W, pixel_bytes, mw1, mh1);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float acc[VEC]; int best[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) { acc[j] = 0.f; best[j] = 0; }
+      if (n[u] > 0) pl[u].value(acc);
+      for (int k = 1; k < n[u]; ++k) {              // two or more pixels per view: not under exact splatting
+        PixLoad<T, PIX, INTERP> nx;
+        nx.issue(fb[u], pix, p0[u] + k, H, W, pixel_bytes, mw1, mh1);
+        float v[VEC];
+        nx.value(v);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          if (RED == DVA_SUM || RED == DVA_MEAN) acc[j] += v[j];
+          else if (RED == DVA_MAX ? v[j] > acc[j] : v[j] < acc[j]) { acc[j] = v[j]; best[j] = k; }
+        }
+      }
+      if (RED == DVA_MEAN && n[u] > 1) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] /= (float)n[u];
+      }
+      if (act[u]) {
+        const int64_t e0 = w[u] * C + (int64_t)ck[u] * VEC;
+        stg_stream16(reinterpret_cast<char*>(out) + e0 * sizeof(T), pack16<T, VEC>(acc));
+        if ((RED == DVA_MAX || RED == DVA_MIN) && arg != nullptr && n[u] >= 2) {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) arg[e0 + j] = p0[u] + best[j];
+        }
+      }
+    }
+  }
+}
+
+// 16-byte vector reduction into global memory (sm_90+): one instruction per four channels
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <typename PIX, bool INTERP, int VEC>
+__device__ __forceinline__ void scatter_chunk(float* __restrict__ gmap_b /* image + chunk offset */,
+                                              const PIX* __restrict__ pix, int64_t p, int C, int H, int W,
+                                              float mw1, float mh1, const float (&g)[VEC]) {
+  const int px = (int)pix[2 * p], py = (int)pix[2 * p + 1];
+  if constexpr (INTERP) {
+    const Bilin q = bilin_setup(px, py, H, W, mw1, mh1);
+    const int64_t o[4] = {((int64_t)q.r0 * W + q.c0) * C, ((int64_t)q.r0 * W + q.c1) * C,
+                          ((int64_t)q.r1 * W + q.c0) * C, ((int64_t)q.r1 * W + q.c1) * C};
+    const float wq[4] = {q.w00, q.w01, q.w10, q.w11};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int j = 0; j < VEC; j += 4)
+        red_add_v4(gmap_b + o[k] + j, wq[k] * g[j], wq[k] * g[j + 1], wq[k] * g[j + 2], wq[k] * g[j + 3]);
+  } else {
+    float* a = gmap_b + ((int64_t)py * W + px) * C;
+#pragma unroll
+    for (int j = 0; j < VEC; j += 4) red_add_v4(a + j, g[j], g[j + 1], g[j + 2], g[j + 3]);
+  }
+}
+
+template <typename T, typename PIX, int LPR, int RED, bool INTERP>
+__global__ void __launch_bounds__(kGpWarps * 32)
+gather_pool_bwd_cl_kernel(const T* __restrict__ gout, const int64_t* __restrict__ img,
+                          const PIX* __restrict__ pix, const int64_t* __restrict__ aptr,
+                          const int64_t* __restrict__ arg, float* __restrict__ gfmap, int C, int H,
+                          int W, int64_t Vw, float mw1, float mh1) {
+  constexpr int VEC = Vec16<T>::N, RPI = 32 / LPR, U = 4;
+  const int lane = threadIdx.x & 31, sg = lane / LPR, lir = lane % LPR;
+  const int cv = C / VEC, tiles = (cv + LPR - 1) / LPR;
+  const int64_t items = Vw * tiles;
+  const int64_t map_elems = (int64_t)H * W * C;
+  const int64_t gwarp = (int64_t)blockIdx.x * kGpWarps + (threadIdx.x >> 5);
+  const int64_t stride = (int64_t)gridDim.x * kGpWarps * RPI * U;
+  for (int64_t it0 = gwarp * RPI * U; it0 < items; it0 += stride) {
+    int64_t w[U], p0[U], b[U]; int n[U], ck[U]; bool act[U];
+    uint4 raw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t item = it0 + u * RPI + sg;
+      act[u] = item < items;
+      w[u] = act[u] ? (tiles == 1 ? item : item / tiles) : 0;
+      ck[u] = (int)(item - w[u] * tiles) * LPR + lir;
+      act[u] = act[u] && ck[u] < cv;
+      p0[u] = aptr[w[u]];
+      n[u] = (int)(aptr[w[u] + 1] - p0[u]);
+      b[u] = img[w[u]];
+      act[u] = act[u] && n[u] > 0;
+      if (act[u]) raw[u] = ldg_stream16(reinterpret_cast<const char*>(gout) + (w[u] * C + (int64_t)ck[u] * VEC) * sizeof(T));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!act[u]) continue;
+      float g[VEC];
+      unpack16<T, VEC>(raw[u], g);
+      if (RED == DVA_MEAN) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) g[j] /= (float)n[u];
+      }
+      const int c0 = ck[u] * VEC;
+      float* gm = gfmap + b[u] * map_elems + c0;
+      if (RED == DVA_MAX || RED == DVA_MIN) {
+        if (n[u] == 1) {
+          scatter_chunk<PIX, INTERP, VEC>(gm, pix, p0[u], C, H, W, mw1, mh1, g);
+        } else {                                    // per-channel winners: scalar atomics
+          const int64_t e0 = w[u] * C + c0;
+#pragma unroll
+          for (int j = 0; j < VEC; ++j)
+            scatter_pixel<true, INTERP>(gfmap, pix, arg[e0 + j], b[u], c0 + j, C, H, W, mw1, mh1, g[j]);
+        }
+      } else {
+        for (int k = 0; k < n[u]; ++k) scatter_chunk<PIX, INTERP, VEC>(gm, pix, p0[u] + k, C, H, W, mw1, mh1, g);
+      }
+    }
+  }
+}
+
+template <typename T> static int gp_cl_lpr(int64_t C) {
+  const int64_t cv = C / Vec16<T>::N;
+  return cv <= 4 ? 4 : (cv <= 8 ? 8 : (cv <= 16 ? 16 : 32));
+}
+template <typename T> static bool gp_cl_vec_ok(const void* map, const void* rows, int64_t C, int64_t H, int64_t W) {
+  return C % Vec16<T>::N == 0 && aligned16(map) && aligned16(rows) && C < (1 << 20) && H * W < (1ll << 31);
+}
+static inline int gp_cl_grid(int64_t items, int rpi, int unroll) {
+  int64_t blocks = (items + (int64_t)kGpWarps * rpi * unroll - 1) / ((int64_t)kGpWarps * rpi * unroll);
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  return (int)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
 }
 
 static inline int gp_grid(int64_t total) {
@@ -133,6 +339,26 @@ template <typename T, typename PIX, bool CL, bool INTERP>
 static int gp_fwd_red(const void* fmap, const int64_t* img, const void* pix, const int64_t* aptr,
                       void* out, int64_t* arg, int64_t C, int64_t H, int64_t W, int64_t Vw,
                       int64_t P, float mw1, float mh1, int reduce, cudaStream_t st) {
+  if constexpr (CL) {
+    if (gp_cl_vec_ok<T>(fmap, out, C, H, W)) {
+      const int lpr = gp_cl_lpr<T>(C);
+      const int64_t cvv = C / Vec16<T>::N;
+      const int64_t items = Vw * ((cvv + lpr - 1) / lpr);
+      const int gridv = gp_cl_grid(items, 32 / lpr, INTERP ? 2 : 4);
+#define GP_FV(R, L) gather_pool_fwd_cl_kernel<T, PIX, L, R, INTERP><<<gridv, kGpWarps * 32, 0, st>>>((const T*)fmap, img, (const PIX*)pix, aptr, (T*)out, arg, (int)C, (int)H, (int)W, Vw, P, mw1, mh1)
+#define GP_FVL(R) do { if (lpr == 4) GP_FV(R, 4); else if (lpr == 8) GP_FV(R, 8); else if (lpr == 16) GP_FV(R, 16); else GP_FV(R, 32); } while (0)
+      switch (reduce) {
+        case DVA_SUM: GP_FVL(DVA_SUM); break;
+        case DVA_MEAN: GP_FVL(DVA_MEAN); break;
+        case DVA_MAX: GP_FVL(DVA_MAX); break;
+        case DVA_MIN: GP_FVL(DVA_MIN); break;
+        default: return fail(DVA_EINVAL, "gather_pool_fwd: unknown reduce");
+      }
+#undef GP_FVL
+#undef GP_FV
+      return check_launch("gather_pool_fwd(cl)");
+    }
+  }
   const int grid = gp_grid(Vw * C);
 #define GP_F(R) gather_pool_fwd_kernel<T, PIX, CL, R, INTERP><<<grid, 256, 0, st>>>((const T*)fmap, img, (const PIX*)pix, aptr, (T*)out, arg, C, H, W, Vw, P, mw1, mh1)
   switch (reduce) {
@@ -150,6 +376,26 @@ template <typename T, typename PIX, bool CL, bool INTERP>
 static int gp_bwd_red(const void* gout, const int64_t* img, const void* pix, const int64_t* aptr,
                       const int64_t* arg, float* gfmap, int64_t C, int64_t H, int64_t W,
                       int64_t Vw, float mw1, float mh1, int reduce, cudaStream_t st) {
+  if constexpr (CL) {
+    if (gp_cl_vec_ok<T>(gfmap, gout, C, H, W) && C % 4 == 0) {
+      const int lpr = gp_cl_lpr<T>(C);
+      const int64_t cvv = C / Vec16<T>::N;
+      const int64_t items = Vw * ((cvv + lpr - 1) / lpr);
+      const int gridv = gp_cl_grid(items, 32 / lpr, 4);
+#define GP_BV(R, L) gather_pool_bwd_cl_kernel<T, PIX, L, R, INTERP><<<gridv, kGpWarps * 32, 0, st>>>((const T*)gout, img, (const PIX*)pix, aptr, arg, gfmap, (int)C, (int)H, (int)W, Vw, mw1, mh1)
+#define GP_BVL(R) do { if (lpr == 4) GP_BV(R, 4); else if (lpr == 8) GP_BV(R, 8); else if (lpr == 16) GP_BV(R, 16); else GP_BV(R, 32); } while (0)
+      switch (reduce) {
+        case DVA_SUM: GP_BVL(DVA_SUM); break;
+        case DVA_MEAN: GP_BVL(DVA_MEAN); break;
+        case DVA_MAX: GP_BVL(DVA_MAX); break;
+        case DVA_MIN: GP_BVL(DVA_MIN); break;
+        default: return fail(DVA_EINVAL, "gather_pool_bwd: unknown reduce");
+      }
+#undef GP_BVL
+#undef GP_BV
+      return check_launch("gather_pool_bwd(cl)");
+    }
+  }
   const int grid = gp_grid(Vw * C);
 #define GP_B(R) gather_pool_bwd_kernel<T, PIX, CL, R, INTERP><<<grid, 256, 0, st>>>((const T*)gout, img, (const PIX*)pix, aptr, arg, gfmap, C, H, W, Vw, mw1, mh1)
   switch (reduce) {

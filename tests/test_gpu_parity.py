@@ -252,6 +252,36 @@ def test_gather_pool_vs_oracle():
                 close(gg, rg, 1e-5, f"gather_pool grad {red}")
 
 
+@pytest.mark.parametrize("C,dtype", [(64, torch.float32), (160, torch.float32), (64, torch.bfloat16),
+                                     (8, torch.float32), (12, torch.float32)])
+def test_gather_pool_channels_last_vector_path(C, dtype):
+    """The 16-byte-chunk kernels of the channels-last layout: mostly one pixel per view (exact
+    splatting: no arg table traffic), some views with several pixels and some with none; rows wider
+    than one warp pass (C = 160) and narrower than a sub-warp (C = 8); C = 12 is the scalar path."""
+    from deepviewagg_b200 import ops
+    gen = torch.Generator().manual_seed(C)
+    B, H, W, Vw = 4, 33, 47, 3000
+    counts = torch.ones(Vw, dtype=torch.long)
+    counts[torch.rand(Vw, generator=gen) < 0.15] = 0
+    counts[torch.rand(Vw, generator=gen) < 0.15] = 3
+    aptr = torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)])
+    P = int(aptr[-1])
+    img = torch.randint(0, B, (Vw,), generator=gen)
+    pix = torch.stack([torch.randint(0, W, (P,), generator=gen), torch.randint(0, H, (P,), generator=gen)], 1)
+    fmap = torch.randn(B, C, H, W, generator=gen).relu().to(dtype).float()
+    w = torch.randn(Vw, C, generator=gen).to(dtype).float()
+    tol, gtol = (1e-6, 1e-5) if dtype == torch.float32 else (8e-3, 1e-5)
+    for red in ("max", "mean", "sum", "min"):
+        fo = fmap.clone().requires_grad_(True)
+        ref = O.segment_csr(O.feature_map_gather(fo, img, pix, aptr), aptr, reduce=red)
+        rg = torch.autograd.grad((ref * w).sum(), fo)[0]
+        fg = fmap.permute(0, 2, 3, 1).contiguous().to(dtype).cuda().requires_grad_(True)
+        got = ops.gather_pool(fg, img.cuda(), pix.to(torch.int16).cuda(), aptr.cuda(), red, channels_last=True)
+        gg = torch.autograd.grad(got, fg, w.to(dtype).cuda())[0].float().permute(0, 3, 1, 2)
+        close(got.float(), ref, tol, f"gather_pool(cl) {red}")
+        close(gg, rg, gtol if dtype == torch.float32 else 8e-3, f"gather_pool(cl) grad {red}")
+
+
 # ------------------------------------------------------------------------------------------------
 # the drop-in modules vs the executed reference (state_dict interchange)
 # ------------------------------------------------------------------------------------------------
