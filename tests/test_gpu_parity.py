@@ -211,7 +211,8 @@ def test_view_attention_zero_points(va_path):
 def test_qk_scores_vs_oracle():
     from deepviewagg_b200 import ops
     gen = torch.Generator().manual_seed(3)
-    for (N, G, D, ds) in ((200, 4, 8, True), (77, 1, 3, False), (50, 8, 2, True)):
+    for (N, G, D, ds) in ((200, 4, 8, True), (77, 1, 3, False), (50, 8, 2, True), (3001, 4, 8, True),
+                         (500, 4, 4, True), (333, 2, 16, False), (100, 8, 16, True)):
         ptr = ragged_ptr(gen, N, 5)
         V = int(ptr[-1])
         k = torch.randn(V, G * D, generator=gen)
