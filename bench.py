@@ -148,15 +148,21 @@ def cpu_step(pr, G):
 
 
 def cpu_pick_size(views, C, G, total_budget_s, n_steps):
-    """Probe at 2000 points, then size the sample so n_steps steps take ~total_budget_s."""
-    probe = 2000
-    pr = cpu_problem(probe, views, C, G)
-    cpu_step(pr, G)
-    t0 = time.perf_counter()
-    cpu_step(pr, G)
-    dt = time.perf_counter() - t0
-    rate = probe / max(dt, 1e-6)                       # points / s
-    n = int(rate * total_budget_s / max(n_steps, 1))
+    """Size the sample so n_steps steps take ~total_budget_s.  The CPU path has a large
+    size-independent cost per step (dozens of small multi-threaded torch ops), so the step time is
+    modelled as a + b * points from two probes (2000 and 6000 points) instead of one rate."""
+    def probe(n):
+        pr = cpu_problem(n, views, C, G)
+        cpu_step(pr, G)
+        t0 = time.perf_counter()
+        cpu_step(pr, G)
+        return time.perf_counter() - t0
+    n1, n2 = 2000, 6000
+    t1, t2 = probe(n1), probe(n2)
+    b = max((t2 - t1) / (n2 - n1), 1e-9)               # seconds per extra point
+    a = max(t1 - b * n1, 0.0)
+    per_step = total_budget_s / max(n_steps, 1)
+    n = int((per_step - a) / b) if per_step > a else n1
     return max(2000, min(n, 200_000))
 
 

@@ -13,6 +13,11 @@ int dva_gemm_run_1_0(const float*, const float*, float*, int, int, int, void*, s
 int dva_gemm_run_1_1(const float*, const float*, float*, int, int, int, void*, size_t, cudaStream_t);
 }
 
+extern "C" int dva_skinny_gemm_supported(int64_t M, int64_t N, int64_t K, int layout);
+extern "C" size_t dva_skinny_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int layout);
+extern "C" int dva_skinny_gemm(const float* A, const float* B, float* D, int64_t M, int64_t N, int64_t K,
+                               int layout, void* workspace, size_t workspace_bytes, void* stream);
+
 using namespace dva;
 
 static bool gemm_shape_ok(int64_t M, int64_t N, int64_t K) {
@@ -20,6 +25,9 @@ static bool gemm_shape_ok(int64_t M, int64_t N, int64_t K) {
 }
 
 extern "C" size_t dva_linear_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int layout, int precision) {
+  // narrow projections (both small dimensions <= 64: every MLP of the map encoders) run on the
+  // exact-fp32 skinny kernels of skinny_gemm.cu whatever the precision mode
+  if (dva_skinny_gemm_supported(M, N, K, layout)) return dva_skinny_gemm_workspace_bytes(M, N, K, layout);
   if (!gemm_shape_ok(M, N, K)) return 0;
   size_t w = 0;
   if (layout == 0) w = precision == 0 ? dva_gemm_ws_0_0((int)M, (int)N, (int)K) : dva_gemm_ws_0_1((int)M, (int)N, (int)K);
@@ -32,6 +40,8 @@ extern "C" int dva_linear_gemm(const float* A, const float* B, float* D, int64_t
                                int layout, int precision, void* workspace, size_t workspace_bytes,
                                void* stream) {
   if (M == 0) return DVA_OK;
+  if (layout >= 0 && layout <= 2 && dva_skinny_gemm_supported(M, N, K, layout))
+    return dva_skinny_gemm(A, B, D, M, N, K, layout, workspace, workspace_bytes, stream);
   if (!gemm_shape_ok(M, N, K)) return fail(DVA_EUNSUPPORTED, "linear_gemm: N and K must be multiples of 4 (16-byte TMA rows)");
   if (layout < 0 || layout > 2 || (precision != 0 && precision != 1)) return fail(DVA_EINVAL, "linear_gemm: bad layout/precision");
   if (!A || !B || !D) return fail(DVA_EINVAL, "linear_gemm: null pointer");

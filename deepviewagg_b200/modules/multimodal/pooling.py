@@ -129,6 +129,16 @@ def _attend(x_mod, compat, csr_idx, num_groups, out_mod, gate, group_scaling, ro
     return x_pool, attentions, gating
 
 
+def _biased_linear(lin, x):
+    """nn.Linear with bias on [rows, K] CUDA fp32 inputs: the projection goes through ops.linear
+    (skinny exact-fp32 kernels for K, N <= 64 -- E_score 32 -> G, Q / K 32 -> G*D), the bias is a
+    broadcast add; same parameters (`weight`, `bias`) as the reference's nn.Linear."""
+    if x.dim() == 2 and ops.tc_gemm_supported(x, lin.weight):
+        z = ops.linear(x, lin.weight)
+        return z if lin.bias is None else z + lin.bias
+    return lin(x)
+
+
 class GroupBimodalCSRPool(nn.Module, _SaveLast):
     """View attention from mapping features only (the paper's model; pooling.py:159-319).
 
@@ -163,9 +173,9 @@ class GroupBimodalCSRPool(nn.Module, _SaveLast):
         x_mod = self.E_mod(x_mod)
         if self.use_mod:
             x_rows = x_mod if row_index is None else x_mod[row_index.long()]
-            compatibilities = self.E_score(self.E_mix(torch.cat([x_map, x_rows], dim=1)))
+            compatibilities = _biased_linear(self.E_score, self.E_mix(torch.cat([x_map, x_rows], dim=1)))
         else:
-            compatibilities = self.E_score(x_map)
+            compatibilities = _biased_linear(self.E_score, x_map)
         x_pool, attentions, gating = _attend(x_mod, compatibilities, csr_idx, self.num_groups,
                                              self.out_mod, self.G, self.group_scaling, row_index)
         if self.save_last:
@@ -222,17 +232,17 @@ class QKVBimodalCSRPool(nn.Module, _SaveLast):
         need_rows = self.use_mod_k or self.use_mod_q
         x_rows = x_mod if (row_index is None or not need_rows) else x_mod[row_index.long()]
         if self.use_mod_k:
-            keys = self.K(self.E_mix_K(torch.cat([x_map, x_rows], dim=1)))
+            keys = _biased_linear(self.K, self.E_mix_K(torch.cat([x_map, x_rows], dim=1)))
         else:
-            keys = self.K(x_map)
+            keys = _biased_linear(self.K, x_map)
         if self.use_mod_q:
             x_main_q = gather_csr(x_main, csr_idx, n_items=x_map.shape[0])
-            queries = self.Q(self.E_mix_Q(torch.cat([x_main_q, x_rows], dim=1)))
+            queries = _biased_linear(self.Q, self.E_mix_Q(torch.cat([x_main_q, x_rows], dim=1)))
             # one query per view: every view is its own segment for the ragged dot kernel
             view_ptr = torch.arange(keys.shape[0] + 1, device=keys.device)
             compatibilities = ops.qk_scores(keys, queries, view_ptr, self.num_groups, self.dim_scaling)
         else:
-            queries = self.Q(x_main)  # N x (D x num_groups); never expanded to views
+            queries = _biased_linear(self.Q, x_main)  # N x (D x num_groups); never expanded to views
             compatibilities = ops.qk_scores(keys, queries, csr_idx, self.num_groups, self.dim_scaling)
         x_pool, attentions, gating = _attend(x_mod, compatibilities, csr_idx, self.num_groups,
                                              self.out_mod, self.G, self.group_scaling, row_index)

@@ -565,8 +565,13 @@ def _tc_gemm(a, b, layout, n_out):
 
 
 def tc_gemm_supported(x, weight):
-    return (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and x.dim() == 2
-            and x.shape[0] > 0 and x.shape[1] % 4 == 0 and weight.shape[0] % 4 == 0)
+    """fp32 [rows, K] x [N, K]: K and N both <= 64 (skinny exact-fp32 kernels, any K / N) or both
+    multiples of 4 (tcgen05 kernels, 16-byte TMA rows)."""
+    if not (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and x.dim() == 2
+            and x.shape[0] > 0):
+        return False
+    K, N = x.shape[1], weight.shape[0]
+    return (K <= 64 and N <= 64) or (K % 4 == 0 and N % 4 == 0)
 
 
 class _Linear(torch.autograd.Function):

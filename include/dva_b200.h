@@ -212,8 +212,13 @@ int dva_neighborhood_features(const float* xyz, const int64_t* neighbors, int km
  *   layout 1: D[M,N] = A[M,K] . B[K,N]     (backward, dX = dZ . weight)
  *   layout 2: D[N,K] = A[M,N]^T . B[M,K]   (backward, dW = dZ^T . X; stream-K over the M rows)
  *   precision 0: fast-FP32 (9 x BF16 split products, fp32-grade accuracy); 1: TF32.
- *   fp32 row-major operands, 16-byte aligned, N % 4 == 0 and K % 4 == 0 (else DVA_EUNSUPPORTED:
- *   the host falls back to a library GEMM).  workspace: dva_linear_gemm_workspace_bytes().
+ *   fp32 row-major operands.  Two kernel families behind the one entry point:
+ *     N <= 64 and K <= 64 (any values; every MLP of the map encoders, pooling.py:645-656): exact-fp32
+ *       "skinny" kernels -- weights in shared memory, one output row per thread, coalesced 16-byte
+ *       global traffic, dW as per-CTA partials reduced in a fixed order; precision is ignored;
+ *     otherwise the tcgen05 kernels: operands 16-byte aligned, N % 4 == 0 and K % 4 == 0 (else
+ *       DVA_EUNSUPPORTED: the host falls back to a library GEMM).
+ *   workspace: dva_linear_gemm_workspace_bytes().
  * ------------------------------------------------------------------------------------------ */
 size_t dva_linear_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int layout, int precision);
 int dva_linear_gemm(const float* A, const float* B, float* D, int64_t M, int64_t N, int64_t K, int layout,

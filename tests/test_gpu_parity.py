@@ -464,7 +464,10 @@ def test_bn_act_vs_torch(R, C):
 # tcgen05 projection GEMM vs an fp64 matmul
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("M,K,N", [(4096, 128, 128), (1000, 64, 64), (37, 8, 32), (50000, 128, 64), (3000, 512, 512),
-                                   (129, 32, 4), (1, 16, 16)])
+                                   (129, 32, 4), (1, 16, 16),
+                                   # skinny kernels (K, N <= 64): the DeepSetFeat layers 8->32, 32->32, 33->32, 64->32
+                                   (70001, 8, 32), (100000, 32, 32), (64123, 33, 32), (30000, 64, 32), (5000, 64, 64),
+                                   (999, 33, 33), (4, 5, 7), (200000, 32, 64), (1500, 3, 1)])
 def test_tc_linear_vs_fp64(M, K, N):
     from deepviewagg_b200 import ops
     gen = torch.Generator().manual_seed(M + K + N)
@@ -484,7 +487,7 @@ def test_tc_linear_vs_fp64(M, K, N):
         close(y, ref, tol, f"linear {mode}")
         close(gx, ref_gx, tol, f"linear grad_x {mode}")
         close(gw, ref_gw, tol, f"linear grad_w {mode}")
-    # shapes the TMA kernel cannot take fall back to the library GEMM, same values
-    x2 = torch.randn(100, 33, generator=gen).cuda()
-    w2 = torch.randn(32, 33, generator=gen).cuda()
+    # wide shapes the TMA kernel cannot take fall back to the library GEMM, same values
+    x2 = torch.randn(100, 130, generator=gen).cuda()
+    w2 = torch.randn(66, 130, generator=gen).cuda()
     close(ops.linear(x2, w2), x2 @ w2.t(), 1e-6, "fallback")

@@ -5,13 +5,15 @@ import torch
 sys.path.insert(0, ".")
 from deepviewagg_b200.modules.multimodal.pooling import GroupBimodalCSRPool
 
-N, v, C = (int(a) for a in (sys.argv[1:4] + [160000, 8, 64][len(sys.argv) - 1:]))
+_args = [a for a in sys.argv[1:] if not a.startswith("--")]
+N, v, C = (int(a) for a in (_args[:3] + [160000, 8, 64][len(_args):]))
+USE_MOD = "--no-mod" not in sys.argv          # the Group-pool YAMLs of the reference set use_mod: False
 dev = "cuda"
 gen = torch.Generator(device=dev).manual_seed(0)
 counts = torch.poisson(torch.full((N,), float(v), device=dev), generator=gen).long()
 ptr = torch.cat([torch.zeros(1, dtype=torch.long, device=dev), counts.cumsum(0)])
 V = int(ptr[-1])
-m = GroupBimodalCSRPool(in_map=8, in_mod=C, num_groups=4, use_num=True).to(dev).train()
+m = GroupBimodalCSRPool(in_map=8, in_mod=C, num_groups=4, use_num=True, use_mod=USE_MOD).to(dev).train()
 x_mod = torch.randn(V, C, device=dev, requires_grad=True)
 x_map = torch.rand(V, 8, device=dev)
 w = torch.randn(N, C, device=dev)
