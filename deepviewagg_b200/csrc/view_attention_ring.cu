@@ -12,7 +12,7 @@
 //     boundaries: one 16-byte cp.async (LDGSTS) per lane and row step, S-1 batches in flight, row
 //     ids prefetched a batch ahead into one register per lane -- no load of the consumer sits on a
 //     dependent-address chain;
-//   * the consumer walks the range in GROUPS of up to 32 points (at most kCapV views):
+//   * the consumer walks the range in GROUPS of up to 32 points (at most 256 / 128 views fwd / bwd):
 //       phase 1  LANE PER POINT: every lane computes the softmax statistics of its own point
 //                (max, first arg-max, denominator, gate) from the fp32 scores and leaves the final
 //                per-view weights e * t / den in a shared tile -- 32 points per instruction;
@@ -22,7 +22,7 @@
 //   * backward: the upstream-gradient rows of the next window of points are fetched by ONE elected
 //     lane with a bulk async copy (cp.async.bulk -> UBLKCP, completion on an mbarrier) -- they are
 //     contiguous in memory, the natural TMA case.
-//   * a point with more than kCapV views (never in the shipped configs) takes a warp-cooperative
+//   * a point with more views than a group holds (never in the shipped configs) takes a warp-cooperative
 //     path: online softmax over the pieces of its segment (forward), raw s' parked in grad_compat
 //     (backward).
 //
@@ -42,17 +42,14 @@ namespace dva {
 #ifndef DVA_RING_PW_BYTES
 #define DVA_RING_PW_BYTES 4096    // backward: bytes of one grad_out window tile (x 2 buffers)
 #endif
-#ifndef DVA_RING_BATCH_BYTES
-#define DVA_RING_BATCH_BYTES 4096
-#endif
 #ifndef DVA_RING_FWD_MINB
-#define DVA_RING_FWD_MINB 10      // CTAs per SM the register budget is sized for (x kRingWarps warps)
+#define DVA_RING_FWD_MINB 12      // CTAs per SM the register budget is sized for (x kRingWarps warps)
 #endif
 #ifndef DVA_RING_BWD_MINB
 #define DVA_RING_BWD_MINB 8
 #endif
 #ifndef DVA_RING_CAPV_FWD
-#define DVA_RING_CAPV_FWD 384     // views per point group (weight tile), multiple of 8
+#define DVA_RING_CAPV_FWD 256     // views per point group (weight tile), multiple of 8
 #endif
 #ifndef DVA_RING_CAPV_BWD
 #define DVA_RING_CAPV_BWD 128
@@ -66,12 +63,20 @@ constexpr uint32_t FULL = 0xffffffffu;
 #endif
 constexpr int kP1Unroll = DVA_RING_P1_UNROLL;   // score loads in flight per lane in the lane-per-point phases
 
-template <int LPR> struct RingGeom {
+// Batch size (measured, tools/bench_shapes.py): forward likes 16 rows per batch for 128/256-byte
+// rows and more resident warps (2 KB batches) for 64- and 512-byte rows; backward 4 KB throughout.
+template <int LPR, bool BWD> struct RingGeom {
   static constexpr int RPI = 32 / LPR;                       // rows per warp step
   static constexpr int RS = LPR * 16;                        // row stride in the ring (bytes)
-  static constexpr int RB = (DVA_RING_BATCH_BYTES / RS) < 32 ? (DVA_RING_BATCH_BYTES / RS) : 32;  // rows per batch
+#ifdef DVA_RING_BATCH_BYTES
+  static constexpr int BATCH = DVA_RING_BATCH_BYTES;
+#else
+  static constexpr int BATCH = BWD ? 4096 : (LPR == 16 ? 4096 : 2048);
+#endif
+  static constexpr int RB = (BATCH / RS) < 32 ? (BATCH / RS) : 32;   // rows per batch
   static constexpr int STEPS = RB / RPI;                     // row steps per batch
   static constexpr int PW = (DVA_RING_PW_BYTES / RS) < 32 ? (DVA_RING_PW_BYTES / RS) : 32;   // points per window (bwd: grad_out tile rows)
+  static constexpr int MINB = BWD ? DVA_RING_BWD_MINB : (BATCH <= 2048 ? 16 : DVA_RING_FWD_MINB);
   static_assert(RB >= RPI && RB % RPI == 0 && (RB & (RB - 1)) == 0, "batch geometry");
 };
 
@@ -127,10 +132,11 @@ __device__ __forceinline__ float sel4(const float4& v, int g) {
 }
 
 // per-warp shared memory (bytes)
-template <int LPR> struct RingSmem {
-  using Gm = RingGeom<LPR>;
+template <int LPR, bool BWD> struct RingSmem {
+  using Gm = RingGeom<LPR, BWD>;
   size_t rows, tile, tile2, rowid, gout, tpt, bars, total;
-  __host__ __device__ RingSmem(bool bwd) {
+  __host__ __device__ RingSmem() {
+    constexpr bool bwd = BWD;
     rows = (size_t)kRingStages * Gm::RB * Gm::RS;
     tile = (size_t)tile_floats(bwd ? DVA_RING_CAPV_BWD : DVA_RING_CAPV_FWD) * sizeof(float);
     tile2 = bwd ? tile : 0;
@@ -156,15 +162,15 @@ __device__ __forceinline__ void load_window(const int64_t* __restrict__ ptr, int
 // forward
 // ---------------------------------------------------------------------------------------------
 template <typename T, int LPR>
-__global__ void __launch_bounds__(kRingWarps * 32, DVA_RING_FWD_MINB)
+__global__ void __launch_bounds__(kRingWarps * 32, RingGeom<LPR, false>::MINB)
 va_ring_fwd_kernel(const VAParams P, const int PR) {
-  using Gm = RingGeom<LPR>;
+  using Gm = RingGeom<LPR, false>;
   constexpr int VEC = Vec16<T>::N, RPI = Gm::RPI, RB = Gm::RB, RS = Gm::RS, S = kRingStages;
   constexpr int G = kRG, CAPV = DVA_RING_CAPV_FWD;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = P.C;
-  const RingSmem<LPR> L(false);
+  const RingSmem<LPR, false> L;
   unsigned char* base = smem_raw + (size_t)warp * L.total;
   unsigned char* rows_s = base;
   float* wt = reinterpret_cast<float*>(base + L.rows);
@@ -436,16 +442,16 @@ va_ring_fwd_kernel(const VAParams P, const int PR) {
 // backward (math: see view_attention.cu; regular group layout only)
 // ---------------------------------------------------------------------------------------------
 template <typename T, int LPR>
-__global__ void __launch_bounds__(kRingWarps * 32, DVA_RING_BWD_MINB)
+__global__ void __launch_bounds__(kRingWarps * 32, RingGeom<LPR, true>::MINB)
 va_ring_bwd_kernel(const VAParams P, const int PR) {
-  using Gm = RingGeom<LPR>;
+  using Gm = RingGeom<LPR, true>;
   constexpr int VEC = Vec16<T>::N, RPI = Gm::RPI, RB = Gm::RB, RS = Gm::RS, S = kRingStages;
   constexpr int G = kRG, CAPV = DVA_RING_CAPV_BWD, PW = Gm::PW;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ float gate_s[kRingWarps][2 * kRG];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = P.C;
-  const RingSmem<LPR> L(true);
+  const RingSmem<LPR, true> L;
   unsigned char* base = smem_raw + (size_t)warp * L.total;
   unsigned char* rows_s = base;
   float* at = reinterpret_cast<float*>(base + L.rows);                // attentions a_vg
@@ -888,7 +894,7 @@ static int ring_launch_geometry(K kern, size_t smem, int64_t N, int max_ctas_per
 
 template <typename T, int LPR>
 static int ring_fwd_launch(const VAParams& P, cudaStream_t st) {
-  const RingSmem<LPR> L(false);
+  const RingSmem<LPR, false> L;
   const size_t smem = L.total * kRingWarps;
   auto kern = va_ring_fwd_kernel<T, LPR>;
   int grid, pr;
@@ -898,7 +904,7 @@ static int ring_fwd_launch(const VAParams& P, cudaStream_t st) {
 }
 template <typename T, int LPR>
 static int ring_bwd_launch(const VAParams& P, int* grid_out, cudaStream_t st) {
-  const RingSmem<LPR> L(true);
+  const RingSmem<LPR, true> L;
   const size_t smem = L.total * kRingWarps;
   auto kern = va_ring_bwd_kernel<T, LPR>;
   int grid, pr;
