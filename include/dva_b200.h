@@ -213,9 +213,10 @@ int dva_neighborhood_features(const float* xyz, const int64_t* neighbors, int km
  *   layout 2: D[N,K] = A[M,N]^T . B[M,K]   (backward, dW = dZ^T . X; stream-K over the M rows)
  *   precision 0: fast-FP32 (9 x BF16 split products, fp32-grade accuracy); 1: TF32.
  *   fp32 row-major operands.  Two kernel families behind the one entry point:
- *     N <= 64 and K <= 64 (any values; every MLP of the map encoders, pooling.py:645-656): exact-fp32
- *       "skinny" kernels -- weights in shared memory, one output row per thread, coalesced 16-byte
- *       global traffic, dW as per-CTA partials reduced in a fixed order; precision is ignored;
+ *     N <= 64 and K <= 64 (any values; every MLP of the map encoders, pooling.py:645-656): "skinny"
+ *       kernels -- weights in shared memory, 128-row tiles double-buffered by cp.async, coalesced
+ *       16-byte global traffic, 3xTF32 split operands on mma.sync (fp32-grade accuracy, ~1e-6), dW
+ *       as per-CTA partials reduced in a fixed order (deterministic); precision is ignored;
  *     otherwise the tcgen05 kernels: operands 16-byte aligned, N % 4 == 0 and K % 4 == 0 (else
  *       DVA_EUNSUPPORTED: the host falls back to a library GEMM).
  *   workspace: dva_linear_gemm_workspace_bytes().
