@@ -238,16 +238,29 @@ skinny_rows_mma_kernel(const float* __restrict__ A, const float* __restrict__ W,
       }
       const uint32_t* bh = wHi + (k0 + tq) * WS + g;
       const uint32_t* bl = wLo + (k0 + tq) * WS + g;
+      // the three products of one output tile depend on each other through its accumulator: issue
+      // them across 2 column blocks x 2 row blocks so that dependent MMAs are 4 apart (small terms first)
+      constexpr int NB = NT >= 2 ? 2 : 1;
 #pragma unroll
-      for (int n = 0; n < NT; ++n) {
-        const uint32_t h0 = bh[n * 8], h1 = bh[4 * WS + n * 8];
-        const uint32_t l0 = bl[n * 8], l1 = bl[4 * WS + n * 8];
+      for (int n = 0; n < NT; n += NB) {
+        uint32_t h0[NB], h1[NB], l0[NB], l1[NB];
 #pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          mma_tf32(acc[m][n], alo[m], h0, h1);       // small terms first
-          mma_tf32(acc[m][n], ahi[m], l0, l1);
-          mma_tf32(acc[m][n], ahi[m], h0, h1);
+        for (int j = 0; j < NB; ++j) {
+          h0[j] = bh[(n + j) * 8]; h1[j] = bh[4 * WS + (n + j) * 8];
+          l0[j] = bl[(n + j) * 8]; l1[j] = bl[4 * WS + (n + j) * 8];
         }
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+#pragma unroll
+          for (int m = 0; m < 2; ++m) mma_tf32(acc[m][n + j], alo[m], h0[j], h1[j]);
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+#pragma unroll
+          for (int m = 0; m < 2; ++m) mma_tf32(acc[m][n + j], ahi[m], l0[j], l1[j]);
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+#pragma unroll
+          for (int m = 0; m < 2; ++m) mma_tf32(acc[m][n + j], ahi[m], h0[j], h1[j]);
       }
     }
     __syncthreads();                                 // every warp is done reading the A tile
@@ -464,17 +477,28 @@ skinny_dw_mma_kernel(const float* __restrict__ A, const float* __restrict__ B, f
           alo[m][q] = to_tf32(v[q] - __uint_as_float(ahi[m][q]));
         }
       }
+      constexpr int NB = (NT >= 2 && MT <= 2) ? 2 : 1;   // dependent MMAs at least 4 apart
 #pragma unroll
-      for (int n = 0; n < NT; ++n) {
-        const float w0 = bp[n * 8], w1 = bp[4 * KP + n * 8];
-        const uint32_t h0 = to_tf32(w0), h1 = to_tf32(w1);
-        const uint32_t l0 = to_tf32(w0 - __uint_as_float(h0)), l1 = to_tf32(w1 - __uint_as_float(h1));
+      for (int n = 0; n < NT; n += NB) {
+        uint32_t h0[NB], h1[NB], l0[NB], l1[NB];
 #pragma unroll
-        for (int m = 0; m < MT; ++m) {
-          mma_tf32(acc[m][n], alo[m], h0, h1);
-          mma_tf32(acc[m][n], ahi[m], l0, l1);
-          mma_tf32(acc[m][n], ahi[m], h0, h1);
+        for (int j = 0; j < NB; ++j) {
+          const float w0 = bp[(n + j) * 8], w1 = bp[4 * KP + (n + j) * 8];
+          h0[j] = to_tf32(w0); h1[j] = to_tf32(w1);
+          l0[j] = to_tf32(w0 - __uint_as_float(h0[j])); l1[j] = to_tf32(w1 - __uint_as_float(h1[j]));
         }
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+#pragma unroll
+          for (int m = 0; m < MT; ++m) mma_tf32(acc[m][n + j], alo[m], h0[j], h1[j]);
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+#pragma unroll
+          for (int m = 0; m < MT; ++m) mma_tf32(acc[m][n + j], ahi[m], l0[j], l1[j]);
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+#pragma unroll
+          for (int m = 0; m < MT; ++m) mma_tf32(acc[m][n + j], ahi[m], h0[j], h1[j]);
       }
     }
   }
