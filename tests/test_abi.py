@@ -43,6 +43,25 @@ def test_abi_version_and_error_string():
     assert lib.dva_view_attention_bwd_workspace_bytes(4) > 0
 
 
+def test_knobs_and_workspace_queries_validate_arguments():
+    lib = _lib.load()
+    # implementation choice of the fused pair: 0 auto, 1 streaming, 2 ring; anything else is refused
+    assert lib.dva_view_attention_set_path(3) == _lib.DVA_EINVAL
+    assert lib.dva_view_attention_set_path(-1) == _lib.DVA_EINVAL
+    for path in (1, 2, 0):
+        assert lib.dva_view_attention_set_path(path) == 0
+    # projection workspace: narrow layers (K, N <= 64) are served by the skinny kernels for any K / N;
+    # only dW (layout 2) needs room for the per-CTA partials
+    assert lib.dva_linear_gemm_workspace_bytes(100000, 32, 33, 0, 0) >= 16
+    small = lib.dva_linear_gemm_workspace_bytes(100000, 32, 33, 2, 0)
+    assert small >= 32 * 33 * 4
+    # wide layers need 16-byte rows for TMA: K % 4 != 0 has no workspace (host falls back to a library GEMM)
+    assert lib.dva_linear_gemm_workspace_bytes(1000, 128, 132, 0, 0) > 0
+    assert lib.dva_linear_gemm_workspace_bytes(1000, 128, 131, 0, 0) == 0
+    rc = lib.dva_linear_gemm(None, None, None, 10, 128, 131, 0, 0, None, 0, None)
+    assert rc == _lib.DVA_EUNSUPPORTED
+
+
 def test_no_cpu_fallback():
     import torch
     from deepviewagg_b200 import ops
