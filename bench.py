@@ -235,6 +235,10 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (printed to
+        # stdout at NCCL_DEBUG=VERSION) out of it unless the caller asked for NCCL logging
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     from deepviewagg_b200 import _lib
