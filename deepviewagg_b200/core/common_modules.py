@@ -3,7 +3,8 @@
 state_dicts load unchanged: `<mlp>.<i>.0.weight`, `<mlp>.<i>.1.batch_norm.{weight,bias,
 running_mean,running_var,num_batches_tracked}`.
 
-The dense projections are plain library GEMMs (cuBLAS through nn.Linear) -- the only
+The dense projections go through ops.linear (3xTF32 mma.sync kernels for K, N <= 64, tcgen05
+kernels for wider layers; cuBLAS only for shapes neither takes) -- the only
 tensor-core work on this path; BatchNorm uses batch statistics over ALL rows in training.
 """
 import torch
