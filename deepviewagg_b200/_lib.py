@@ -51,6 +51,7 @@ SIGNATURES = {
                                    _i64, _i64, _i64, _i64, _i32, _i32, _vp]),
     "dva_interp_pool_bwd": (_i32, [_vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _i64,
                                    _i64, _i64, _i64, _i64, _i32, _i32, _vp]),
+    "dva_transpose_last2": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp]),
     "dva_knn_cell_ids": (_i32, [_vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _i32, _i32, _vp]),
     "dva_knn_grid": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _f32, _f32, _i32, _i32, _i32,
                             _vp, _vp, _vp]),

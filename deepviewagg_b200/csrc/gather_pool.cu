@@ -501,3 +501,49 @@ extern "C" int dva_interp_pool_bwd(const void* grad_out, int channels_last, cons
   return gather_pool_bwd_impl<true>("interp_pool_bwd", grad_out, channels_last, img, pix, pix_is_i16,
                                     aptr, arg, grad_fmap, B, C, H, W, map_w, map_h, Vw, P, reduce, dtype, stream);
 }
+
+// ---------------------------------------------------------------------------------------------
+// [B, R, S] -> [B, S, R] (NCHW <-> NHWC with R = C, S = H*W or the reverse): lets the reference's
+// NCHW-contiguous feature maps use the channels-last gather / scatter kernels when a large share of
+// the map is gathered.  32 x 32 shared tiles, both sides coalesced.
+// ---------------------------------------------------------------------------------------------
+namespace dva {
+template <typename T>
+__global__ void __launch_bounds__(256)
+transpose_last2_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t R, int64_t S) {
+  __shared__ T tile[32][33];
+  const int64_t b = blockIdx.z;
+  const int64_t s0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8 threads
+  const T* sb = src + b * R * S;
+  T* db = dst + b * R * S;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int64_t r = r0 + ty + j, s = s0 + tx;
+    if (r < R && s < S) tile[ty + j][tx] = sb[r * S + s];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int64_t s = s0 + ty + j, r = r0 + tx;
+    if (r < R && s < S) db[s * R + r] = tile[tx][ty + j];
+  }
+}
+}  // namespace dva
+
+extern "C" int dva_transpose_last2(const void* src, void* dst, int64_t B, int64_t R, int64_t S, int dtype,
+                                   void* stream) {
+  if (B < 0 || R < 0 || S < 0) return fail(DVA_EINVAL, "transpose_last2: negative size");
+  if (B == 0 || R == 0 || S == 0) return DVA_OK;
+  if (!src || !dst) return fail(DVA_EINVAL, "transpose_last2: null pointer");
+  if (B > 65535 || (R + 31) / 32 > 65535) return fail(DVA_EUNSUPPORTED, "transpose_last2: batch / row count too large");
+  const dim3 grid((unsigned)((S + 31) / 32), (unsigned)((R + 31) / 32), (unsigned)B);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case DVA_F32: transpose_last2_kernel<float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, R, S); break;
+    case DVA_BF16:
+    case DVA_F16: transpose_last2_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)src, (uint16_t*)dst, R, S); break;
+    default: return fail(DVA_EINVAL, "transpose_last2: unknown dtype");
+  }
+  return check_launch("transpose_last2");
+}

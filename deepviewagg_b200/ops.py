@@ -10,7 +10,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import REDUCE_CODES, check, dtype_code, ptr, require_cuda, stream_ptr
+from ._lib import DTYPE_CODES, REDUCE_CODES, check, dtype_code, ptr, require_cuda, stream_ptr
 
 
 def _as_2d(src):
@@ -388,16 +388,37 @@ def heuristic_pool(x_mod, x_map, csr_idx, feat, mode="max"):
 # --------------------------------------------------------------------------------------------
 # fused feature-map gather + atomic pool (image.py:1285 + pooling.py:63)
 # --------------------------------------------------------------------------------------------
+def _transpose_last2(t, B, R, S):
+    """[B,R,S] -> [B,S,R] copy through dva_transpose_last2 (t contiguous)."""
+    out = torch.empty_like(t)
+    with torch.cuda.device(t.device):
+        check(_lib.load().dva_transpose_last2(ptr(t), ptr(out), B, R, S, dtype_code(t), stream_ptr()),
+              "dva_transpose_last2")
+    return out
+
+
+# NCHW maps: when at least this share of the map's pixels is gathered, one transposition to
+# channels-last (2 x map bytes) beats reading every element through its own 32-byte sector
+_NCHW_TRANSPOSE_SHARE = 0.25
+
+
 class _GatherPool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, fmap, images, pixels, atomic_ptr, reduce, channels_last, mapping_size):
         require_cuda(fmap, images, pixels, atomic_ptr)
         lib = _lib.load()
         fmap = fmap.contiguous()
+        via_cl = False
         if channels_last:
             B, H, W, C = fmap.shape
         else:
             B, C, H, W = fmap.shape
+            n_corner = 1 if mapping_size is None else 4
+            if (fmap.dtype in DTYPE_CODES and C % (16 // fmap.element_size()) == 0 and B <= 65535
+                    and pixels.shape[0] * n_corner >= _NCHW_TRANSPOSE_SHARE * B * H * W):
+                # the reference's layout (image.py:1884): transpose once, then the channels-last kernels
+                fmap = _transpose_last2(fmap, B, C, H * W).view(B, H, W, C)
+                channels_last, via_cl = True, True
         images = images.long().contiguous()
         if pixels.dtype not in (torch.int16, torch.int32):
             pixels = pixels.int()
@@ -415,7 +436,7 @@ class _GatherPool(torch.autograd.Function):
             else:
                 check(lib.dva_interp_pool_fwd(*head, int(mapping_size[0]), int(mapping_size[1]), *tail),
                       "dva_interp_pool_fwd")
-        ctx.cfg = (B, C, H, W, Vw, P, code, bool(channels_last), fmap.shape, fmap.dtype, mapping_size)
+        ctx.cfg = (B, C, H, W, Vw, P, code, bool(channels_last), fmap.shape, fmap.dtype, mapping_size, via_cl)
         ctx.save_for_backward(images, pixels, atomic_ptr, arg)
         return out
 
@@ -423,7 +444,7 @@ class _GatherPool(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
         images, pixels, atomic_ptr, arg = ctx.saved_tensors
-        B, C, H, W, Vw, P, code, cl, shape, dt, mapping_size = ctx.cfg
+        B, C, H, W, Vw, P, code, cl, shape, dt, mapping_size, via_cl = ctx.cfg
         lib = _lib.load()
         grad_out = grad_out.contiguous()
         gf = torch.zeros(shape, dtype=torch.float32, device=grad_out.device)
@@ -436,6 +457,8 @@ class _GatherPool(torch.autograd.Function):
             else:
                 check(lib.dva_interp_pool_bwd(*head, int(mapping_size[0]), int(mapping_size[1]), *tail),
                       "dva_interp_pool_bwd")
+        if via_cl:      # gradient of the NCHW input: transpose the channels-last map gradient back
+            gf = _transpose_last2(gf, B, H * W, C).view(B, C, H, W)
         return gf.to(dt), None, None, None, None, None, None
 
 

@@ -159,6 +159,11 @@ int dva_gather_pool_bwd(const void* grad_out, int channels_last, const int64_t* 
                         float* grad_fmap, int64_t B, int64_t C, int64_t H, int64_t W, int64_t Vw,
                         int64_t P, int reduce, int dtype, void* stream);
 
+/* [B,R,S] -> [B,S,R] layout change (dtype-sized elements), e.g. the reference's NCHW-contiguous
+ * feature maps (image.py:1884 indexes them as x[b, :, y, x]) to channels-last and map gradients back,
+ * so that dva_gather_pool_* / dva_interp_pool_* can run their 16-byte-chunk channels-last kernels. */
+int dva_transpose_last2(const void* src, void* dst, int64_t B, int64_t R, int64_t S, int dtype, void* stream);
+
 /* I5b  bilinear variant: the `interpolate=True` branch of get_mapped_features
  *   replaces image.py:1278-1283 -> sparse_interpolation (image.py:105-170, padding 'border')
  *   followed by the same atomic pool.  pix are at the MAPPING resolution (map_w, map_h); every

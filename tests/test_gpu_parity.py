@@ -283,6 +283,35 @@ def test_gather_pool_channels_last_vector_path(C, dtype):
         close(gg, rg, gtol if dtype == torch.float32 else 8e-3, f"gather_pool(cl) grad {red}")
 
 
+@pytest.mark.parametrize("interp", [False, True])
+def test_gather_pool_nchw_through_transposition(interp):
+    """NCHW maps of which a large share is gathered are transposed once to channels-last
+    (dva_transpose_last2) and pooled by the vector kernels; same values and map gradient as the
+    direct NCHW kernels (sparse gather of the same map: below the share threshold)."""
+    from deepviewagg_b200 import ops
+    gen = torch.Generator().manual_seed(77)
+    B, C, H, W = 3, 32, 37, 53
+    fmap = torch.randn(B, C, H, W, generator=gen).relu().cuda()
+    for Vw in (40, 4000):                              # 40 views: direct NCHW kernels; 4000: transposed
+        counts = torch.randint(0, 3, (Vw,), generator=gen)
+        aptr = torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)])
+        P = int(aptr[-1])
+        img = torch.randint(0, B, (Vw,), generator=gen)
+        msz = (2 * W, 2 * H) if interp else (W, H)
+        pix = torch.stack([torch.randint(0, msz[0], (P,), generator=gen), torch.randint(0, msz[1], (P,), generator=gen)], 1)
+        w = torch.randn(Vw, C, generator=gen).cuda()
+        res = []
+        for cl in (False, True):
+            f = (fmap.permute(0, 2, 3, 1).contiguous() if cl else fmap.clone()).requires_grad_(True)
+            args = (f, img.cuda(), pix.to(torch.int16).cuda(), aptr.cuda())
+            out = ops.interp_pool(*args, msz, "max", channels_last=cl) if interp else ops.gather_pool(*args, "max", channels_last=cl)
+            g = torch.autograd.grad(out, f, w)[0]
+            res.append((out, g.permute(0, 3, 1, 2) if cl else g))
+        assert torch.equal(res[0][0], res[1][0])
+        close(res[0][1], res[1][1], 1e-6, "map gradient")
+        assert res[0][1].shape == fmap.shape and res[0][1].is_contiguous()
+
+
 # ------------------------------------------------------------------------------------------------
 # the drop-in modules vs the executed reference (state_dict interchange)
 # ------------------------------------------------------------------------------------------------
