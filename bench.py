@@ -342,18 +342,20 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        n_cpu = cpu_pick_size(v, C, G, total_budget_s=15.0, n_steps=3)
+        # ~30 s of CPU work: one warm-up and one timed step of ~15 s each (the CPU path carries seconds
+        # of size-independent cost per step, so a larger sample is the favourable one for it)
+        n_cpu = cpu_pick_size(v, C, G, total_budget_s=30.0, n_steps=2)
         pr = cpu_problem(n_cpu, v, C, G)
         cpu_step(pr, G)
         t0 = time.perf_counter()
-        reps = 2
+        reps = 1
         for _ in range(reps):
             cpu_step(pr, G)
         dt = (time.perf_counter() - t0) / reps
         cpu_baseline = {"value": n_cpu / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{n_cpu} points x {v} views x {C} ch fp32, fwd+bwd, oracle port of "
                                   f"pooling.py:285-300 + modules.py:518 on torch CPU ({cores} threads), "
-                                  f"mean of {reps} after 1 warm-up"}
+                                  f"{reps} timed step after 1 warm-up"}
 
     if rank == 0:
         line = {
