@@ -34,6 +34,28 @@ import torch  # noqa: E402
 METRIC = "Mpoints/s through view-agg fwd+bwd"
 UNIT = "Mpoints/s"
 
+# stdout carries exactly ONE line, the JSON result.  Libraries write to file descriptor 1 behind
+# Python's back (NCCL prints "NCCL version ..." there at communicator creation), so fd 1 is pointed
+# at stderr for the whole run and the result goes to a private duplicate of the original stdout.
+_RESULT_FD = None
+
+
+def capture_stdout():
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, line)
+
 
 def parse():
     p = argparse.ArgumentParser()
@@ -192,7 +214,7 @@ def run_reference_arm(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world):
@@ -220,6 +242,7 @@ def ncu_traffic(args):
 # ---------------------------------------------------------------------------------------------------
 def main():
     args = parse()
+    capture_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -235,10 +258,6 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (printed to
-        # stdout at NCCL_DEBUG=VERSION) out of it unless the caller asked for NCCL logging
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     from deepviewagg_b200 import _lib
@@ -366,7 +385,7 @@ def main():
             "gpu_launches": int(launches), "roofline": roofline, "roofline_detail": extra_roof,
             "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
