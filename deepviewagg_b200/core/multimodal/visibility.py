@@ -37,13 +37,32 @@ def pose_to_rotation_matrix(opk):
     return torch.from_numpy(np.dot(m_o, np.dot(m_p, m_k)).astype(np.float32))
 
 
+def _inv4_f32(E):
+    """float32 inverse of the 4x4 extrinsic exactly as numba's np.linalg.inv computes it
+    (visibility.py:233): LAPACK sgetrf + sgetri (numpy's own inv solves against the identity with
+    sgesv instead and differs in the last bit, which moves ~40 % of the float pixel coordinates
+    by one ulp).  Host-side camera set-up, once per image."""
+    try:
+        from scipy.linalg import lapack
+    except ImportError as e:  # pragma: no cover - scipy ships with the image (numba needs it too)
+        raise ImportError("the 'scannet' camera needs scipy's LAPACK bindings for a bit-exact "
+                          "camera-to-world matrix") from e
+    lu, piv, info = lapack.sgetrf(E)
+    if info != 0:
+        raise np.linalg.LinAlgError("singular extrinsic matrix")
+    inv, info = lapack.sgetri(lu, piv)
+    if info != 0:
+        raise np.linalg.LinAlgError("singular extrinsic matrix")
+    return np.ascontiguousarray(inv, dtype=np.float32)
+
+
 def _camera_transform(camera, img_extrinsic):
     """(A, t0, t1) float32 with p = A (xyz - t0) + t1 (visibility.py:231-244, 304-310)."""
     E = np.ascontiguousarray(np.asarray(
         img_extrinsic.detach().cpu().numpy() if isinstance(img_extrinsic, torch.Tensor) else img_extrinsic,
         dtype=np.float32))
     if camera == 'scannet':
-        c2w = np.linalg.inv(E)
+        c2w = _inv4_f32(E)
         return c2w[:3, :3].copy(), np.zeros(3, np.float32), c2w[:3, 3].copy()
     return E[:3, :3].T.copy(), E[:3, 3].copy(), np.zeros(3, np.float32)
 
@@ -134,7 +153,8 @@ def fisheye_splat_boxes(x_proj, y_proj, xyz, img_extrinsic, img_intrinsic_fishey
     lib = _lib.load()
     xyz = xyz.float().contiguous()
     m = xyz.shape[0]
-    d = torch.sqrt((xyz ** 2).sum(dim=1))                                   # float32, like norm_cpu
+    # norm_cpu: float32, squares summed left to right (a device-side reduction may associate otherwise)
+    d = torch.sqrt((xyz[:, 0] * xyz[:, 0] + xyz[:, 1] * xyz[:, 1]) + xyz[:, 2] * xyz[:, 2])
     swell = 1 + k_swell * torch.exp(-d.double() / np.log(d_swell))          # float64, like numba
     top = xyz.clone()
     top[:, 2] += (swell * voxel / 2).float()                                # z_offset is float32
@@ -220,7 +240,8 @@ def postprocess_features(xyz_to_img, y_proj, dist, linearity, planarity, scatter
             features.append(f)
     if xyz_to_img is not None and dist is not None and normals is not None:
         u = (xyz_to_img / (dist + 1e-4).reshape((-1, 1))).float()
-        features.append((u * normals.float()).sum(dim=1).abs())
+        p = u * normals.float()
+        features.append(((p[:, 0] + p[:, 1]) + p[:, 2]).abs())           # torch CPU's sum order over 3 terms
     if y_proj is not None:
         features.append((y_proj / img_size[1]).float())
     return torch.stack(features).t()

@@ -12,6 +12,7 @@
 // HBM-bound integer work: 8 B atomic per covered pixel; the [W,Hc] uint64 map (4 MB at
 // 1024x512) lives in L2.
 #include "dva_common.cuh"
+#include "libm_f32.h"
 
 namespace dva {
 
@@ -21,8 +22,12 @@ constexpr unsigned long long kEmpty = 0xffffffffffffffffull;
 // pose = [img_xyz(3), R(9 row-major)] fp32 on device; R = pose_to_rotation_matrix (host mirror).
 // numba semantics reproduced: xyz, dist, v, t, p are float32; every expression that mixes a
 // float32 array with a Python float (np.pi) is evaluated in float64 (that is why the reference
-// returns float64 pixel coordinates, visibility.py:250-252).  Trigonometry is evaluated in
-// fp64 and rounded once to fp32, which reproduces a correctly-rounded libm float result.
+// returns float64 pixel coordinates, visibility.py:250-252).  Bit-exactness of the pixel indices
+// needs two more facts, both measured on the executed reference (oracle/make_golden.py fixtures):
+//  * `xyz_to_img.dot(rotation.transpose())` is a BLAS sgemm whose k-loop is a chain of fused
+//    multiply-adds in k order: v = fma(dz, r2, fma(dy, r1, dx * r0));
+//  * np.arctan2 / np.arccos on float32 are libm's atan2f / acosf, which are NOT correctly rounded;
+//    libm_f32.h reproduces glibc's float-only evaluation operation by operation.
 __global__ void __launch_bounds__(256)
 project_equirect_kernel(const float* __restrict__ xyz, const float* __restrict__ pose,
                         float* __restrict__ dist, double* __restrict__ x_proj,
@@ -40,11 +45,11 @@ project_equirect_kernel(const float* __restrict__ xyz, const float* __restrict__
     const float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
     dist[i] = d;
     // v = xyz_to_img . R^T (float32)
-    const float v0 = __fadd_rn(__fadd_rn(__fmul_rn(dx, R[0]), __fmul_rn(dy, R[1])), __fmul_rn(dz, R[2]));
-    const float v1 = __fadd_rn(__fadd_rn(__fmul_rn(dx, R[3]), __fmul_rn(dy, R[4])), __fmul_rn(dz, R[5]));
-    const float v2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, R[6]), __fmul_rn(dy, R[7])), __fmul_rn(dz, R[8]));
-    const float t = (float)atan2((double)v1, (double)v0);
-    const float p = (float)acos((double)__fdiv_rn(v2, d));
+    const float v0 = __fmaf_rn(dz, R[2], __fmaf_rn(dy, R[1], __fmul_rn(dx, R[0])));
+    const float v1 = __fmaf_rn(dz, R[5], __fmaf_rn(dy, R[4], __fmul_rn(dx, R[3])));
+    const float v2 = __fmaf_rn(dz, R[8], __fmaf_rn(dy, R[7], __fmul_rn(dx, R[6])));
+    const float t = dva_atan2f(v1, v0);
+    const float p = dva_acosf(__fdiv_rn(v2, d));
     double w = ((double)(W - 1) * (1.0 - (double)t / PI) / 2.0);
     double h = ((double)(H - 1) * (double)p / PI);
     w = w - floor(w / (double)W) * (double)W;      // numpy/python '%': result has divisor's sign
@@ -81,9 +86,10 @@ project_camera_kernel(const float* __restrict__ xyz, const float* __restrict__ c
     const float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
     dist[i] = d;
     const float q0 = px - t0[0], q1 = py - t0[1], q2 = pz - t0[2];
-    const float p0 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(A[0], q0), __fmul_rn(A[1], q1)), __fmul_rn(A[2], q2)), t1[0]);
-    const float p1 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(A[3], q0), __fmul_rn(A[4], q1)), __fmul_rn(A[5], q2)), t1[1]);
-    const float p2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(A[6], q0), __fmul_rn(A[7], q1)), __fmul_rn(A[8], q2)), t1[2]);
+    // R @ xyz.T is an sgemm: fused multiply-add chain in k order (see project_equirect_kernel), then "+ T"
+    const float p0 = __fadd_rn(__fmaf_rn(A[2], q2, __fmaf_rn(A[1], q1, __fmul_rn(A[0], q0))), t1[0]);
+    const float p1 = __fadd_rn(__fmaf_rn(A[5], q2, __fmaf_rn(A[4], q1, __fmul_rn(A[3], q0))), t1[1]);
+    const float p2 = __fadd_rn(__fmaf_rn(A[8], q2, __fmaf_rn(A[7], q1, __fmul_rn(A[6], q0))), t1[2]);
     double x, y, z;
     if (camera == 1) {
       x = (double)__fadd_rn(__fdiv_rn(__fmul_rn(p0, in[0]), p2), in[2]);

@@ -194,6 +194,7 @@ def main():
     make_interp_golden(ref)
     make_neighborhood_golden(ref)
     make_camera_golden(ref)
+    make_visibility_model_golden(ref)
 
 
 def make_camera_golden(ref):
@@ -249,6 +250,54 @@ def make_camera_golden(ref):
              pin=c["pin"] if c["pin"] is not None else np.zeros(0), fish=c["fish"] if c["fish"] is not None else np.zeros(0),
              size=np.array(c["size"]), crop=np.array(c["crop"]), r=np.array([0.3, 8.0]),
              proj_idx=idx, dist=dist, x_proj=xp, y_proj=yp, **extra)
+
+
+def make_visibility_model_golden(ref):
+    """Z4 / Z5: the assembled dict of SplattingVisibility.__call__ (visibility.py:1677-1776) --
+    idx, x, y, depth and the [k, 6] viewing-condition features of postprocess_features
+    (:1548-1582: normalised depth, linearity, planarity, scattering, |cos(view, normal)|,
+    normalised pixel height) -- executed on the CPU (numba) path for the three camera families."""
+    vis = ref.visibility
+    gen = torch.Generator().manual_seed(29)
+    n = 7000
+    xyz = (torch.rand(n, 3, generator=gen) - 0.5) * torch.tensor([12., 12., 4.])
+    geo = torch.rand(n, 3, generator=gen)
+    normals = torch.nn.functional.normalize(torch.randn(n, 3, generator=gen), dim=1)
+    img_xyz = torch.tensor([0.3, -0.2, 0.1])
+    c2w = np.eye(4)
+    a, b, c = -1.4, 0.1, 0.5
+    rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+    rz = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
+    c2w[:3, :3] = rz @ ry @ rx
+    c2w[:3, 3] = img_xyz.numpy()
+    intr = np.eye(4, dtype=np.float32)
+    intr[0, 0], intr[1, 1], intr[0, 2], intr[1, 2] = 250.0, 250.0, 159.5, 119.5
+    fish = torch.tensor([2.2134, 0.016798, 0.7572, 1336.3, 1335.7, 716.94, 705.76])
+    cases = {
+        "equirect_exact": (dict(voxel=0.05, exact=True, img_size=(512, 256), crop_top=16, crop_bottom=24, r_max=8,
+                                r_min=0.5, camera="s3dis_equirectangular"),
+                           dict(img_opk=torch.tensor([0.05, -0.1, 0.7]))),
+        "equirect_splat": (dict(voxel=0.05, exact=False, img_size=(512, 256), crop_top=0, crop_bottom=0, r_max=8,
+                                r_min=0.5, camera="s3dis_equirectangular"),
+                           dict(img_opk=torch.tensor([0.05, -0.1, 0.7]))),
+        "scannet": (dict(voxel=0.03, exact=True, img_size=(320, 240), r_max=8, r_min=0.3, camera="scannet"),
+                    dict(img_extrinsic=torch.from_numpy(np.linalg.inv(c2w)).float(),
+                         img_intrinsic_pinhole=torch.from_numpy(intr))),
+        "kitti360_fisheye": (dict(voxel=0.05, exact=True, img_size=(1400, 1400), r_max=8, r_min=0.3,
+                                  camera="kitti360_fisheye"),
+                             dict(img_extrinsic=torch.from_numpy(c2w).float(), img_intrinsic_fisheye=fish)),
+    }
+    for tag, (ctor, call) in cases.items():
+        model = vis.SplattingVisibility(**ctor)
+        out = model(xyz, img_xyz, linearity=geo[:, 0], planarity=geo[:, 1], scattering=geo[:, 2],
+                    normals=normals, **call)
+        arrays = dict(xyz=xyz, img_xyz=img_xyz, geo=geo, normals=normals,
+                      ctor_keys=np.array(list(ctor.keys())), **{"ctor/" + k: np.asarray(v) for k, v in ctor.items()},
+                      **{"call/" + k: v for k, v in call.items()},
+                      **{"out/" + k: v for k, v in out.items()})
+        print(tag, {k: tuple(v.shape) for k, v in out.items()})
+        save("visibility_model_" + tag, **arrays)
 
 
 def toy_settings(gen, n_points, specs, F=8):
@@ -458,4 +507,10 @@ def make_integer_golden(ref):
 
 
 if __name__ == "__main__":
-    main()
+    # `--only f1,f2` regenerates single fixture families without touching the others
+    if len(sys.argv) > 2 and sys.argv[1] == "--only":
+        _ref = ref_loader.load_reference()
+        for _name in sys.argv[2].split(","):
+            globals()[_name](_ref)
+    else:
+        main()

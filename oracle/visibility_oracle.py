@@ -62,7 +62,10 @@ def camera_transform(camera, img_extrinsic):
     """(A, t0, t1) with p = A (xyz - t0) + t1, float32 (visibility.py:231-244, 304-310)."""
     E = np.ascontiguousarray(np.asarray(img_extrinsic, dtype=np.float32))
     if camera == "scannet":
-        c2w = np.linalg.inv(E)
+        # numba's np.linalg.inv = LAPACK sgetrf + sgetri (numpy's inv uses sgesv: last-bit differences)
+        from scipy.linalg import lapack
+        lu, piv, _ = lapack.sgetrf(E)
+        c2w = np.ascontiguousarray(lapack.sgetri(lu, piv)[0], dtype=np.float32)
         return c2w[:3, :3].copy(), np.zeros(3, np.float32), c2w[:3, 3].copy()
     return E[:3, :3].T.copy(), E[:3, 3].copy(), np.zeros(3, np.float32)
 
@@ -146,6 +149,66 @@ def zbuffer(splat, dist, x_proj, y_proj, W, H, crop_top=0, crop_bottom=0, exact=
 
 
 # ---- lexicographic helpers (utils/multimodal.py) ---------------------------------------------------
+def postprocess_features(xyz_to_img, y_proj, dist, linearity, planarity, scattering, normals, img_size,
+                         r_max, r_min):
+    """visibility.py:1548-1582 (+ normalize_dist_cuda :1503-1518, orientation_cuda :1521-1545): the
+    [k, F] float32 viewing-condition features.  torch CPU float32 arithmetic restated in numpy."""
+    f32 = np.float32
+    feats = []
+    if dist is not None:
+        d = np.asarray(dist, f32)
+        feats.append(((d - f32(r_min)) / f32(r_max + 1e-4)).astype(f32))
+    for f in (linearity, planarity, scattering):
+        if f is not None:
+            feats.append(np.asarray(f, f32))
+    if xyz_to_img is not None and dist is not None and normals is not None:
+        u = (np.asarray(xyz_to_img, f32) / (np.asarray(dist, f32) + f32(1e-4)).reshape(-1, 1)).astype(f32)
+        p = u * np.asarray(normals, f32)
+        feats.append(np.abs((p[:, 0] + p[:, 1]) + p[:, 2]).astype(f32))
+    if y_proj is not None:
+        feats.append((np.asarray(y_proj, np.float64) / img_size[1]).astype(f32))
+    return np.stack(feats).T
+
+
+def splatting_visibility(xyz, img_xyz, linearity=None, planarity=None, scattering=None, normals=None,
+                         img_opk=None, img_extrinsic=None, img_intrinsic_pinhole=None,
+                         img_intrinsic_fisheye=None, img_size=(1024, 512), crop_top=0, crop_bottom=0, r_max=30,
+                         r_min=0.5, camera="s3dis_equirectangular", voxel=0.1, k_swell=1.0, d_swell=1000,
+                         exact=False):
+    """SplattingVisibility.__call__ (visibility.py:1677-1776): projection -> splat boxes -> z-buffer ->
+    features, assembled exactly like VisibilityModel.__call__ :1694-1757."""
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    img_xyz = np.asarray(img_xyz, np.float32)
+    W, H = int(img_size[0]), int(img_size[1])
+    if camera == "s3dis_equirectangular":
+        R = pose_to_rotation_matrix(np.asarray(img_opk, np.float32))
+        dist, xp, yp, keep = project_equirect(xyz, img_xyz, R, W, H, crop_top, crop_bottom, r_min, r_max)
+    else:
+        intr = img_intrinsic_fisheye if camera == "kitti360_fisheye" else img_intrinsic_pinhole
+        dist, xp, yp, keep = project_camera(xyz, img_xyz, camera, img_extrinsic, np.asarray(intr), W, H, crop_top,
+                                            crop_bottom, r_min, r_max)
+    idx_1 = np.where(keep)[0]
+    if idx_1.size == 0:
+        e = np.zeros(0, np.int64)
+        return dict(idx=e, x=e.copy(), y=e.copy(), depth=np.zeros(0, np.float32), features=np.zeros(0, np.float32))
+    dist, xp, yp = dist[idx_1], xp[idx_1], yp[idx_1]
+    if camera == "s3dis_equirectangular":
+        sp = splat_boxes(xp, yp, dist, W, H, crop_top, crop_bottom, voxel, k_swell, d_swell)
+    elif camera == "kitti360_fisheye":
+        sp = fisheye_splat(xp, yp, xyz[idx_1], img_extrinsic, np.asarray(img_intrinsic_fisheye), W, H, crop_top,
+                           crop_bottom, voxel, k_swell, d_swell)
+    else:
+        K = np.asarray(img_intrinsic_pinhole, np.float32)
+        sp = splat_boxes(xp, yp, dist, W, H, crop_top, crop_bottom, voxel, k_swell, d_swell, camera="pinhole",
+                         fx=float(K[0, 0]), fy=float(K[1, 1]))
+    idx_2, x_pix, y_pix, _ = zbuffer(sp, dist, xp, yp, W, H, crop_top, crop_bottom, exact=exact)
+    idx = idx_1[idx_2]
+    pick = lambda a: None if a is None else np.asarray(a)[idx]  # noqa: E731
+    feats = postprocess_features(xyz[idx] - img_xyz, yp[idx_2], dist[idx_2], pick(linearity), pick(planarity),
+                                 pick(scattering), pick(normals), (W, H), r_max, r_min)
+    return dict(idx=idx, x=x_pix, y=y_pix, depth=dist[idx_2], features=feats)
+
+
 def _composite(*arrays):
     """CompositeNDArray (utils/multimodal.py:175-250): key = sum a_i * prod_{j>i} (max_j + 1)."""
     arrays = [np.asarray(a).astype(np.int64) for a in arrays]
