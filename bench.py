@@ -8,7 +8,14 @@ Workload (named in config.workload): the synthetic stress case the metric is quo
 1 M points x 32 views x 128 channels fp32 per GPU, Group-pool variant (scores given), gating on,
 group scaling on, rows gathered through a random permutation (worst-case locality).
 One step = one fused forward + one fused backward over one batch.  Weak scaling: every rank owns an
-independent batch; the only collective is the NCCL all-reduce of the gate-parameter gradients.
+independent batch; the only collective is the NCCL all-reduce of the pool-parameter gradient bucket
+(~160 KB -- the gate gradients the kernels produce live at its head), issued on a side
+stream so that it overlaps the next step's forward.
+
+Timing: a measurement is EXACTLY --steps steps between two CUDA events, bracketed by a barrier and a
+device synchronisation on both sides, max over ranks.  That measurement is repeated (`rounds`, sized
+so that the timed regions add up to >= 2.5 s) and the MEDIAN round is reported; every round, the mean
+and per-rank step statistics are in `consistency`.
 
 value : device-resident throughput (inputs in HBM), CUDA events, max over ranks.
 e2e   : the same step through the host-buffer API (deepviewagg_b200.host_api): pinned host inputs
@@ -70,6 +77,7 @@ def parse():
     p.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
     p.add_argument("--idx", default="randperm", choices=["randperm", "arange", "none"])
     p.add_argument("--counts", default="uniform", choices=["uniform", "ragged"])
+    p.add_argument("--rounds", type=int, default=0, help="timed repetitions of the K-step region (0 = from a 2.5 s budget)")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
     return p.parse_args()
@@ -101,49 +109,78 @@ _REASONS = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_pow
 
 
 class ClockSampler:
-    def __init__(self, gpu_index):
-        self.gpu, self.proc, self.path = gpu_index, None, None
+    """SM clocks / throttle reasons of the given GPUs, sampled in-process through NVML from a
+    background thread of rank 0 (no nvidia-smi children: at N = 8 eight of them initialising NVML
+    inside a sub-second timed window was one of the round-1 scaling suspects).  start() is called
+    >= 2 s before the timed region; mark()/unmark() delimit the samples that count as "under load"."""
+
+    def __init__(self, gpu_indices, period_s=0.05):
+        self.gpus, self.period = list(gpu_indices), period_s
+        self.rows, self._stop, self._thread, self._on = [], None, None, False
+        self.backend = None
+
+    def _loop_nvml(self):
+        import pynvml as nv
+        hs = [nv.nvmlDeviceGetHandleByIndex(i) for i in self.gpus]
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        mx = [nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM) for h in hs]
+        while not self._stop.is_set():
+            for g, h, m in zip(self.gpus, hs, mx):
+                try:
+                    sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    self.rows.append((self._on, g, float(sm), float(m), [k for k, b in bits.items() if r & b]))
+                except Exception:
+                    pass
+            self._stop.wait(self.period)
 
     def start(self):
+        import threading
+        self._stop = threading.Event()
         try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={_Q}", "--format=csv,noheader,nounits", "-lms", "50",
-                 "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            import pynvml as nv
+            nv.nvmlInit()
+            self.backend = "nvml (in-process thread, rank 0)"
+            self._thread = threading.Thread(target=self._loop_nvml, daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc = None
+            self.backend = None
+
+    def mark(self):
+        self._on = True
+
+    def unmark(self):
+        self._on = False
 
     def stop(self):
-        rows = []
-        try:
-            if self.proc is not None:
-                self.proc.terminate()
-                self.proc.wait(timeout=5)
-            if self.path:
-                rows = [r for r in open(self.path).read().splitlines() if r.strip()]
-                os.unlink(self.path)
-            if not rows:  # region shorter than one sampling period: one immediate query
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={_Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=20)
-                rows = [r for r in out.stdout.splitlines() if r.strip()]
-        except Exception:
-            pass
-        sm, mx, reasons = [], [], set()
-        for r in rows:
-            f = [c.strip() for c in r.split(",")]
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=5)
+        rows = [r for r in self.rows if r[0]] or self.rows
+        if not rows:  # NVML unavailable: one immediate nvidia-smi query so the key is never empty
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-                for name, val in zip(_REASONS, f[4:8]):
-                    if val == "Active":
-                        reasons.add(name)
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={_Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=30)
+                for r in out.stdout.splitlines():
+                    f = [c.strip() for c in r.split(",")]
+                    if f and f[0].isdigit() and int(f[0]) in self.gpus:
+                        rows.append((True, int(f[0]), float(f[1]), float(f[2]),
+                                     [n for n, v in zip(_REASONS, f[4:8]) if v == "Active"]))
+                self.backend = "nvidia-smi (one query after the timed region)"
             except Exception:
-                continue
-        if not sm:
+                pass
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        per_gpu = {}
+        for _, g, sm, _, _ in rows:
+            per_gpu.setdefault(g, []).append(sm)
+        return {"sm_mhz": statistics.median(r[2] for r in rows), "sm_max_mhz": max(r[3] for r in rows),
+                "reasons": sorted({x for r in rows for x in r[4]}), "samples": len(rows),
+                "per_gpu_sm_mhz_median": {str(g): statistics.median(v) for g, v in sorted(per_gpu.items())},
+                "source": self.backend}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -169,33 +206,50 @@ def cpu_step(pr, G):
     torch.autograd.grad(out, [x, c, gw, gb], grad_outputs=pr["gout"])
 
 
-def cpu_pick_size(views, C, G, total_budget_s, n_steps):
-    """Size the sample so n_steps steps take ~total_budget_s.  The CPU path has a large
-    size-independent cost per step (dozens of small multi-threaded torch ops), so the step time is
-    modelled as a + b * points from two probes (2000 and 6000 points) instead of one rate."""
-    def probe(n):
-        pr = cpu_problem(n, views, C, G)
+REFERENCE_SAMPLE_POINTS = 100_000     # fixed: identical `config` on every box and at every N
+
+
+def cpu_threads():
+    """Threads the CPU arm may really use: logical CPUs this process is allowed on, capped by the
+    cgroup CPU quota (os.cpu_count() reports the host's CPUs even inside a limited container)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
+def cpu_best_threads(views, C, G):
+    """The reference arm gets its best thread count: a quick probe (one warm step + one timed step of
+    20 000 points each) at {all, 64, 32, 16} allowed threads.  Round 1 ran 128 threads over dozens of
+    small torch ops and measured seconds of size-independent cost per step; the sample itself is fixed."""
+    avail = cpu_threads()
+    cands = sorted({t for t in (avail, 64, 32, 16) if t <= avail}, reverse=True)
+    if len(cands) == 1:
+        return cands[0], {}
+    pr = cpu_problem(20_000, views, C, G)
+    probe = {}
+    for t in cands:
+        torch.set_num_threads(t)
         cpu_step(pr, G)
         t0 = time.perf_counter()
         cpu_step(pr, G)
-        return time.perf_counter() - t0
-    n1, n2 = 2000, 6000
-    t1, t2 = probe(n1), probe(n2)
-    b = max((t2 - t1) / (n2 - n1), 1e-9)               # seconds per extra point
-    a = max(t1 - b * n1, 0.0)
-    per_step = total_budget_s / max(n_steps, 1)
-    n = int((per_step - a) / b) if per_step > a else n1
-    return max(2000, min(n, 200_000))
+        probe[t] = time.perf_counter() - t0
+    best = min(probe, key=probe.get)
+    return best, {str(k): round(v, 3) for k, v in probe.items()}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     C, G, v = args.channels, args.groups, args.views
-    n = cpu_pick_size(v, C, G, total_budget_s=90.0, n_steps=args.steps + args.warmup)
+    threads, probe = cpu_best_threads(v, C, G)
+    torch.set_num_threads(threads)
+    n = REFERENCE_SAMPLE_POINTS
     pr = cpu_problem(n, v, C, G)
     for _ in range(args.warmup):
         cpu_step(pr, G)
@@ -204,13 +258,15 @@ def run_reference_arm(args):
         cpu_step(pr, G)
     dt = time.perf_counter() - t0
     val = n * args.steps / dt / 1e6
-    sample = f"{n} points x {v} views x {C} ch fp32 per step, fwd+bwd, torch CPU {torch.get_num_threads()} threads"
+    sample = (f"{n} points x {v} views x {C} ch fp32 per step (fixed sample), fwd+bwd, oracle port of "
+              f"pooling.py:285-300 + modules.py:518 on torch CPU, {threads} threads (best of probe {probe})")
+    cfg = workload_config(args, int(os.environ.get("WORLD_SIZE", str(args.gpus))))   # the GPU arm's config, verbatim
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(args, 1),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -223,6 +279,7 @@ def workload_config(args, world):
                         f"group_scaling, idx={args.idx}, counts={args.counts}",
             "points_per_gpu": args.points, "views": args.views, "channels": args.channels,
             "groups": args.groups, "idx": args.idx, "counts": args.counts, "parallelism": f"dp{world}",
+            "sample_points": REFERENCE_SAMPLE_POINTS,   # points per step of the CPU reference arm / cpu_baseline leg
             "l2": "inputs (>16 GB per step) exceed the 126 MB L2; no explicit flush needed"}
 
 
@@ -254,6 +311,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from deepviewagg_b200.distributed import bind_to_gpu_numa_node
+    numa_info = bind_to_gpu_numa_node(local)         # CPU affinity + memory policy before any pinned allocation
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -289,52 +348,135 @@ def main():
     plan.gout.copy_(torch.randn(N, C, device=dev, generator=gen).to(tdtype))
     torch.cuda.synchronize()
 
-    def step():
-        plan.forward_device()
-        plan.backward_device()
-        if dist is not None:  # the path's only exchange: parameter gradients
-            dist.all_reduce(plan.ggate)
+    # ---- the path's only exchange: the pool-parameter gradient bucket ------------------
+    # GroupBimodalCSRPool(in_map=8, in_mod=C, G) has 40 236 parameters at C = 128 (161 KB fp32); the
+    # kernels of this step produce the last 2*G of them (G.weight, G.bias), written straight into the
+    # bucket; the rest stands in for the encoder gradients a full model step would add.  Two buckets
+    # alternate so that the all-reduce of step k (side stream) overlaps forward + backward of step k+1.
+    n_bucket = 2 * C * C + 4 * C + 7212 + 2 * G      # E_mod (2 layers + BN) + E_map/E_score + gate
+    buckets = [torch.zeros(n_bucket, dtype=torch.float32, device=dev) for _ in range(2)]
+    gate_views = [bk[n_bucket - 2 * G:].view(2, G) for bk in buckets]
+    side = torch.cuda.Stream(device=dev) if dist is not None else None
+    ar_done = [None, None]
+    main_stream = torch.cuda.current_stream(dev)
+    step_no = [0]
 
-    for _ in range(max(args.warmup, 3)):
+    def step(ev=None):
+        k = step_no[0] % 2
+        step_no[0] += 1
+        if ev is not None:
+            ev[0].record()
+        plan.forward_device()
+        if ev is not None:
+            ev[1].record()
+        if ar_done[k] is not None:                      # bucket k is being reduced since step-2
+            main_stream.wait_event(ar_done[k])
+        plan.ggate = gate_views[k]
+        plan.backward_device()
+        if ev is not None:
+            ev[2].record()
+        if dist is not None:
+            side.wait_stream(main_stream)
+            with torch.cuda.stream(side):
+                dist.all_reduce(buckets[k])
+                ar_done[k] = torch.cuda.Event()
+                ar_done[k].record(side)
+
+    def drain():
+        if side is not None:
+            main_stream.wait_stream(side)
+
+    W_ = max(args.warmup, 3)
+    for _ in range(W_):
         step()
+    drain()
     torch.cuda.synchronize()
 
     K = args.steps
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    # one measurement = exactly K steps; rounds sized so that the timed regions total >= 2.5 s
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local)
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    launches0 = _lib.launch_count()
-    sampler.start()
     e0.record()
-    for k in range(K):
-        ev[k][0].record()
-        plan.forward_device()
-        ev[k][1].record()
-        plan.backward_device()
-        ev[k][2].record()
-        if dist is not None:
-            dist.all_reduce(plan.ggate)
+    for _ in range(K):
+        step()
+    drain()
     e1.record()
     torch.cuda.synchronize()
-    clocks = sampler.stop()
-    launches = _lib.launch_count() - launches0
+    probe_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if dist is not None:
-        dist.barrier()
-    elapsed_ms = e0.elapsed_time(e1)
-    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(probe_ms, op=dist.ReduceOp.MAX)
+    rounds = args.rounds if args.rounds > 0 else int(min(40, max(3, -(-2500.0 // float(probe_ms.item())))))
+
+    sampler = ClockSampler(list(range(int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))) if world > 1
+                           else [local]) if rank == 0 else None
+    if sampler is not None:
+        sampler.start()
+    # >= 2 s of the same work before the first timed round: the sampler is up, clocks are settled
+    t_pre = time.perf_counter()
+    while time.perf_counter() - t_pre < 2.0:
+        for _ in range(K):
+            step()
+        drain()
+        torch.cuda.synchronize()
+
+    ev = [[[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)] for _ in range(rounds)]
+    round_ms = []
+    launches = 0
+    for r in range(rounds):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        launches0 = _lib.launch_count()
+        if sampler is not None:
+            sampler.mark()
+        e0.record()
+        for k in range(K):
+            step(ev[r][k])
+        drain()                                          # the last all-reduces finish inside the region
+        e1.record()
+        torch.cuda.synchronize()
+        if sampler is not None:
+            sampler.unmark()
+        launches = _lib.launch_count() - launches0
+        if dist is not None:
+            dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        round_ms.append(float(t.item()))
+    clocks = sampler.stop() if sampler is not None else None
     pts = torch.tensor([float(N)], device=dev, dtype=torch.float64)
     if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(pts, op=dist.ReduceOp.SUM)
-    elapsed_ms = float(t.item())
     total_points = float(pts.item())
+    elapsed_ms = statistics.median(round_ms)
     value = total_points * K / (elapsed_ms * 1e-3) / 1e6
 
-    fwd_ms = statistics.mean(ev[k][0].elapsed_time(ev[k][1]) for k in range(K))
-    bwd_ms = statistics.mean(ev[k][1].elapsed_time(ev[k][2]) for k in range(K))
+    # per-rank step statistics (ms, event-timed start of step k -> start of step k+1) so a straggler is named
+    own = []
+    for r in range(rounds):
+        for k in range(K - 1):
+            own.append(ev[r][k][0].elapsed_time(ev[r][k + 1][0]))
+    own_t = torch.tensor([min(own), statistics.median(own), max(own)] if own else [0.0, 0.0, 0.0],
+                         device=dev, dtype=torch.float64)
+    if dist is not None:
+        allr = [torch.zeros_like(own_t) for _ in range(world)]
+        dist.all_gather(allr, own_t)
+    else:
+        allr = [own_t]
+    per_rank = [{"rank": i, "min": float(t[0]), "median": float(t[1]), "max": float(t[2])} for i, t in enumerate(allr)]
+    consistency = {"rounds": rounds, "steps_per_round": K, "round_ms": round_ms,
+                   "timed_region_s": sum(round_ms) * 1e-3,
+                   "mean_ms_per_step": sum(round_ms) / (rounds * K), "median_ms_per_step": elapsed_ms / K,
+                   "min_ms_per_step": min(round_ms) / K, "max_ms_per_step": max(round_ms) / K,
+                   "per_rank_step_ms": per_rank,
+                   "allreduce": {"elements": n_bucket, "bytes": 4 * n_bucket,
+                                 "where": "side stream, overlaps the next step; drained inside the timed region"}
+                   if dist is not None else None,
+                   "numa": numa_info}
+
+    flat = [e for r in ev for e in r]
+    fwd_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in flat)
+    bwd_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in flat)
     b_fwd, b_bwd = algorithmic_bytes(N, V, C, G, s)
     peak, peak_src = hbm_peak()
     ach_bwd = b_bwd / (bwd_ms * 1e-3) / 1e9
@@ -355,42 +497,41 @@ def main():
     # ---- e2e: host buffers, copies inside the timed region ---------------------------------------
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, plan, dist, dev, world, N, V)
+        e2e = run_e2e(args, plan, dist, dev, world, N, V, n_bucket)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        # ~30 s of CPU work: one warm-up and one timed step of ~15 s each (the CPU path carries seconds
-        # of size-independent cost per step, so a larger sample is the favourable one for it)
-        n_cpu = cpu_pick_size(v, C, G, total_budget_s=30.0, n_steps=2)
+        # bounded sample: one warm-up + two timed steps of the reference arm's fixed 100 000-point sample
+        threads, probe = cpu_best_threads(v, C, G)
+        torch.set_num_threads(threads)
+        n_cpu = REFERENCE_SAMPLE_POINTS
         pr = cpu_problem(n_cpu, v, C, G)
         cpu_step(pr, G)
+        reps = 2
         t0 = time.perf_counter()
-        reps = 1
         for _ in range(reps):
             cpu_step(pr, G)
         dt = (time.perf_counter() - t0) / reps
-        cpu_baseline = {"value": n_cpu / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"{n_cpu} points x {v} views x {C} ch fp32, fwd+bwd, oracle port of "
-                                  f"pooling.py:285-300 + modules.py:518 on torch CPU ({cores} threads), "
-                                  f"{reps} timed step after 1 warm-up"}
+        cpu_baseline = {"value": n_cpu / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"{n_cpu} points x {v} views x {C} ch fp32 (fixed sample), fwd+bwd, oracle port "
+                                  f"of pooling.py:285-300 + modules.py:518 on torch CPU, {threads} threads (best "
+                                  f"of probe {probe}), {reps} timed steps after 1 warm-up"}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
-            "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / K, "higher_is_better": True,
+            "warmup": W_, "ms_per_step": elapsed_ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": workload_config(args, world), "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(launches), "roofline": roofline, "roofline_detail": extra_roof,
-            "cpu_baseline": cpu_baseline,
+            "cpu_baseline": cpu_baseline, "consistency": consistency,
         }
         emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
-def run_e2e(args, plan, dist, dev, world, N, V):
+def run_e2e(args, plan, dist, dev, world, N, V, n_bucket):
     """Same step through the host-buffer API. Pinned buffers for the whole batch (x alone is
     V*C*s bytes); if the host cannot hold them the e2e leg is skipped with a reason."""
     try:
@@ -420,7 +561,11 @@ def run_e2e(args, plan, dist, dev, world, N, V):
     for k, h in ins.items():           # fill the caller-side buffers with this rank's data
         h.copy_(getattr(plan, k))
     torch.cuda.synchronize()
-    reduce_grads = (lambda p: dist.all_reduce(p.ggate)) if dist is not None else None
+    # every slot reduces its own full-size parameter-gradient bucket (gate gradients at the tail)
+    for pl in pipe.plans:
+        pl.bucket = torch.zeros(n_bucket, dtype=torch.float32, device=dev)
+        pl.ggate = pl.bucket[n_bucket - 2 * args.groups:].view(2, args.groups)
+    reduce_grads = (lambda p: dist.all_reduce(p.bucket)) if dist is not None else None
 
     def timed(n_steps, use_depth):
         """n_steps full host-buffer steps; returns (ms, h2d, d2h)."""

@@ -9,6 +9,7 @@ fixture metadata.  The GPU box has no /root/reference: tests only read the commi
 """
 import os
 import sys
+import types
 
 os.environ.setdefault("PYTORCH_JIT", "0")
 
@@ -195,6 +196,7 @@ def main():
     make_neighborhood_golden(ref)
     make_camera_golden(ref)
     make_visibility_model_golden(ref)
+    make_block_down_golden(ref)
 
 
 def make_camera_golden(ref):
@@ -360,6 +362,125 @@ def make_branch_golden(ref, interpolate=False, name="unimodal_branch_toy"):
     grads = {"grad/" + n: (g if g is not None else torch.zeros(1)) for n, g in zip(names, gs)}
     save(name, x_3d=x_3d, w=w, out=out["x_3d"], x_seen=out["x_seen"],
          csr=mod.view_cat_csr_indexing, n_points=np.array(N), **arrays, **sd0, **grads)
+
+
+class _StubSampler:
+    last_idx = None
+
+
+class _PickBlock(torch.nn.Module):
+    """Dense 3D block with a `.sampler` (modules.py:131-141): keeps the rows `idx` of its input."""
+
+    def __init__(self, idx):
+        super().__init__()
+        self.sampler = _StubSampler()
+        self.idx = idx
+
+    def forward(self, x):
+        self.sampler.last_idx = self.idx
+        return x[self.idx]
+
+
+class _FakeCoordsManager:
+    def __init__(self, src, target):
+        self.src, self.target = src, target
+
+    def get_coords_map(self, stride_in, stride_out):
+        return self.src, self.target
+
+
+class _FakeSparseTensor:
+    """The three attributes forward_3d_block_down reads from a MinkowskiEngine tensor
+    (modules.py:146-158): F, tensor_stride, coords_man.get_coords_map."""
+
+    def __init__(self, F, stride, coords_man):
+        self.F, self.tensor_stride, self.coords_man = F, [stride], coords_man
+
+
+class _StridedBlock(torch.nn.Module):
+    """Fake strided sparse conv: parent feature = mean of its children's, stride doubles."""
+
+    def __init__(self, parent):
+        super().__init__()
+        self.parent = parent
+
+    def forward(self, x):
+        n_out = int(self.parent.max()) + 1
+        F = torch.zeros(n_out, x.F.shape[1]).index_add_(0, self.parent, x.F)
+        cnt = torch.zeros(n_out).index_add_(0, self.parent, torch.ones(self.parent.numel()))
+        return _FakeSparseTensor(F / cnt.clamp(min=1).unsqueeze(1), x.tensor_stride[0] * 2, x.coords_man)
+
+
+def _dump_mappings(mod, prefix):
+    out = {}
+    for s, im in enumerate(mod):
+        m = im.mappings
+        out[f"{prefix}s{s}_pointers"] = m.pointers
+        out[f"{prefix}s{s}_images"] = m.images
+        out[f"{prefix}s{s}_atomic_pointers"] = m.values[1].pointers
+        out[f"{prefix}s{s}_pixels"] = m.pixels
+        out[f"{prefix}s{s}_features"] = m.features
+        out[f"{prefix}s{s}_num_views"] = np.array(im.num_views)
+    return out
+
+
+def make_block_down_golden(ref):
+    """U2: MultimodalBlockDown.forward_3d_block_down (modules.py:101-236) EXECUTED on a non-Identity
+    block: (a) a dense block with a sampler -> 'pick' re-indexing of x_seen and of every setting's
+    mappings; (b) a strided sparse block -> child->parent index from the coordinate map, x_seen
+    scatter (:225) and ImageData.select_points(idx, 'merge') (image.py:2211-2273)."""
+    I, M = ref.image, ref.modules
+    gen = torch.Generator().manual_seed(9090)
+    N, C3 = 600, 6
+    specs = [(64, 32, 3, 2.2), (48, 48, 2, 1.6)]
+    settings = toy_settings(gen, N, specs)
+
+    def build():
+        ims = []
+        for s, st in enumerate(settings):
+            im = I.SameSettingImageData(path=np.array([f"img_{s}_{i}" for i in range(st["n_img"])]),
+                                        pos=torch.zeros(st["n_img"], 3), opk=torch.zeros(st["n_img"], 3),
+                                        ref_size=(st["W"], st["H"]), proj_upscale=1, downscale=1)
+            im.mappings = I.ImageMapping.from_dense(st["pid"], st["iid"], st["pix"], st["feat"], num_points=N)
+            ims.append(im)
+        return I.ImageData(ims)
+
+    arrays = {"n_points": np.array(N)}
+    for s, st in enumerate(settings):
+        for k in ("pid", "iid", "pix", "feat"):
+            arrays[f"s{s}_{k}"] = st[k]
+        arrays[f"s{s}_size"] = np.array([st["W"], st["H"], st["n_img"]])
+    x_3d = torch.randn(N, C3, generator=gen)
+    x_seen = torch.rand(N, generator=gen) < 0.6
+    arrays["x_3d"], arrays["x_seen"] = x_3d, x_seen
+
+    # (a) 'pick': N indices with repetitions (the reference compares against arange(N), so the
+    # sampler must return as many indices as there are input points, modules.py:133-140)
+    pick_idx = torch.randint(0, N, (N,), generator=gen)
+    d = M.MultimodalBlockDown.forward_3d_block_down(
+        {"x_3d": x_3d.clone(), "x_seen": x_seen.clone(), "modalities": {"image": build()}}, _PickBlock(pick_idx))
+    arrays["pick_idx"] = pick_idx
+    arrays["pick_x_3d"], arrays["pick_x_seen"] = d["x_3d"], d["x_seen"]
+    arrays.update(_dump_mappings(d["modalities"]["image"], "pick_"))
+
+    # (b) 'merge' through a fake MinkowskiEngine tensor: children in shuffled order in the coords map
+    n_out = 170
+    parent = torch.randint(0, n_out, (N,), generator=gen)
+    parent[:n_out] = torch.arange(n_out)                      # every parent voxel has a child
+    src = torch.randperm(N, generator=gen)
+    cm = _FakeCoordsManager(src, parent[src])
+    M.me = types.SimpleNamespace(SparseTensor=_FakeSparseTensor)
+    try:
+        d = M.MultimodalBlockDown.forward_3d_block_down(
+            {"x_3d": _FakeSparseTensor(x_3d.clone(), 1, cm), "x_seen": x_seen.clone(),
+             "modalities": {"image": build()}}, _StridedBlock(parent))
+    finally:
+        M.me = None
+    arrays["merge_parent"], arrays["merge_src"] = parent, src
+    arrays["merge_x_3d"] = d["x_3d"].F
+    arrays["merge_x_seen"] = d["x_seen"] > 0 if d["x_seen"].dtype != torch.bool else d["x_seen"]
+    arrays.update(_dump_mappings(d["modalities"]["image"], "merge_"))
+    save("block_down", **arrays)
 
 
 def make_interp_golden(ref):

@@ -60,6 +60,50 @@ def test_two_rank_sharding_and_grad_allreduce():
         assert torch.allclose(x, (a + b) / 2, atol=1e-6) and torch.equal(x, y)
 
 
+def _worker_missing(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from deepviewagg_b200 import distributed as D
+    ps = [torch.nn.Parameter(torch.zeros(3)), torch.nn.Parameter(torch.zeros(2, 2)),
+          torch.nn.Parameter(torch.zeros(5), requires_grad=False), torch.nn.Parameter(torch.zeros(1))]
+    # rank 0: gradients for p0 and p1; rank 1 (batch without modality data): only p0.  p3 is unused
+    # on both ranks, p2 is frozen.
+    ps[0].grad = torch.full((3,), 1.0 + rank)
+    if rank == 0:
+        ps[1].grad = torch.full((2, 2), 4.0)
+    n = D.allreduce_gradients(ps, average=True)
+    q.put((rank, n, [None if p.grad is None else p.grad.reshape(-1).tolist() for p in ps]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bucket_layout_does_not_depend_on_local_grads():
+    """ranks with different sets of existing gradients must still reduce one identical
+    bucket (zeros for missing ones) instead of hanging or mis-aligning."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_missing, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, n, grads in res:
+        assert n == 3 + 4 + 1                               # every requires_grad parameter, frozen one excluded
+        assert grads[0] == [1.5] * 3                        # (1 + 2) / 2
+        assert grads[1] == [2.0] * 4                        # (4 + 0) / 2 on BOTH ranks
+        assert grads[2] is None and grads[3] == [0.0]
+
+
+def test_numa_binding_is_best_effort():
+    from deepviewagg_b200 import distributed as D
+    assert D._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    info = D.bind_to_gpu_numa_node(0)                       # no GPU here: reports the error, never raises
+    assert isinstance(info, dict) and "node" in info
+
+
 def test_single_process_is_a_noop():
     from deepviewagg_b200 import distributed as D
     p = torch.nn.Parameter(torch.ones(3))
