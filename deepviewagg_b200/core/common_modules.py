@@ -4,7 +4,7 @@ state_dicts load unchanged: `<mlp>.<i>.0.weight`, `<mlp>.<i>.1.batch_norm.{weigh
 running_mean,running_var,num_batches_tracked}`.
 
 The dense projections go through ops.linear (3xTF32 mma.sync kernels for K, N <= 64, tcgen05
-kernels for wider layers; cuBLAS only for shapes neither takes) -- the only
+kernels for wider layers, widths that are not a multiple of 4 zero-padded) -- the only
 tensor-core work on this path; BatchNorm uses batch statistics over ALL rows in training.
 """
 import torch
@@ -45,7 +45,9 @@ class MLPLayer(nn.Sequential):
             return super().forward(x)
         slope = act.negative_slope if isinstance(act, nn.LeakyReLU) else (0.0 if isinstance(act, nn.ReLU) else 1.0)
         from .. import ops
-        z = ops.linear(x, lin.weight) if lin.bias is None else lin(x)   # tcgen05 GEMM when shapes allow
+        z = ops.linear(x, lin.weight)
+        if lin.bias is not None:
+            z = z + lin.bias
         return ops.batch_norm_act(z, bn.batch_norm, negative_slope=slope)
 
 

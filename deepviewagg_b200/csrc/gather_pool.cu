@@ -46,22 +46,30 @@ __device__ __forceinline__ int64_t fmap_off(int64_t b, int64_t c, int64_t y, int
   return CL ? (((b * H + y) * W + x) * C + c) : (((b * C + c) * H + y) * W + x);
 }
 
+// Memory safety (the reference's x[feature_map_indexing] raises IndexError on a stale or mis-scaled
+// mapping; a kernel cannot raise): pixel coordinates and image ids are clamped into the map, so a bad
+// mapping can never read or -- in backward -- atomically write outside the feature-map tensor.
+// ops.gather_pool(check_indices=True) / DVA_CHECK_INDICES=1 validates them up front and raises.
+__device__ __forceinline__ int clamp_px(int v, int n) { return v < 0 ? 0 : (v >= n ? n - 1 : v); }
+__device__ __forceinline__ int64_t clamp_img(int64_t b, int64_t B) { return b < 0 ? 0 : (b >= B ? B - 1 : b); }
+
 template <typename T, typename PIX, bool CL, int RED, bool INTERP>
 __global__ void __launch_bounds__(256)
 gather_pool_fwd_kernel(const T* __restrict__ fmap, const int64_t* __restrict__ img,
                        const PIX* __restrict__ pix, const int64_t* __restrict__ aptr,
                        T* __restrict__ out, int64_t* __restrict__ arg, int64_t C, int64_t H,
-                       int64_t W, int64_t Vw, int64_t P, float mw1, float mh1) {
+                       int64_t W, int64_t Vw, int64_t P, float mw1, float mh1, int64_t B) {
   const int64_t total = Vw * C;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t w = t / C, c = t - w * C;
     const int64_t p0 = aptr[w], p1 = aptr[w + 1];
-    const int64_t b = img[w];
+    const int64_t b = clamp_img(img[w], B);
     float acc = 0.f;
     int64_t best = P;
     for (int64_t p = p0; p < p1; ++p) {
-      const int64_t px = (int64_t)pix[2 * p], py = (int64_t)pix[2 * p + 1];
+      int64_t px = (int64_t)pix[2 * p], py = (int64_t)pix[2 * p + 1];
+      if (!INTERP) { px = clamp_px((int)px, (int)W); py = clamp_px((int)py, (int)H); }
       float v;
       if (INTERP) {
         const Bilin q = bilin_setup((int)px, (int)py, (int)H, (int)W, mw1, mh1);
@@ -90,7 +98,8 @@ template <bool CL, bool INTERP, typename PIX>
 __device__ __forceinline__ void scatter_pixel(float* __restrict__ gfmap, const PIX* __restrict__ pix,
                                               int64_t p, int64_t b, int64_t c, int64_t C, int64_t H,
                                               int64_t W, float mw1, float mh1, float g) {
-  const int64_t px = (int64_t)pix[2 * p], py = (int64_t)pix[2 * p + 1];
+  int64_t px = (int64_t)pix[2 * p], py = (int64_t)pix[2 * p + 1];
+  if (!INTERP) { px = clamp_px((int)px, (int)W); py = clamp_px((int)py, (int)H); }
   if (INTERP) {
     const Bilin q = bilin_setup((int)px, (int)py, (int)H, (int)W, mw1, mh1);
     atomicAdd(gfmap + fmap_off<CL>(b, c, q.r0, q.c0, C, H, W), q.w00 * g);
@@ -107,14 +116,14 @@ __global__ void __launch_bounds__(256)
 gather_pool_bwd_kernel(const T* __restrict__ gout, const int64_t* __restrict__ img,
                        const PIX* __restrict__ pix, const int64_t* __restrict__ aptr,
                        const int64_t* __restrict__ arg, float* __restrict__ gfmap, int64_t C,
-                       int64_t H, int64_t W, int64_t Vw, float mw1, float mh1) {
+                       int64_t H, int64_t W, int64_t Vw, float mw1, float mh1, int64_t B) {
   const int64_t total = Vw * C;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t w = t / C, c = t - w * C;
     const int64_t p0 = aptr[w], p1 = aptr[w + 1];
     if (p1 <= p0) continue;
-    const int64_t b = img[w];
+    const int64_t b = clamp_img(img[w], B);
     float g = Cvt<T>::to_f(gout[t]);
     if (RED == DVA_MEAN) g /= (float)(p1 - p0);
     if (RED == DVA_MAX || RED == DVA_MIN) {
@@ -141,7 +150,8 @@ template <typename T, typename PIX, bool INTERP> struct PixLoad {
   // fb: map of the view's image + this lane's chunk offset (bytes); pixel_bytes = C * sizeof(T)
   __device__ __forceinline__ void issue(const char* __restrict__ fb, const PIX* __restrict__ pix, int64_t p,
                                         int H, int W, uint32_t pixel_bytes, float mw1, float mh1) {
-    const int px = (int)pix[2 * p], py = (int)pix[2 * p + 1];
+    int px = (int)pix[2 * p], py = (int)pix[2 * p + 1];
+    if constexpr (!INTERP) { px = clamp_px(px, W); py = clamp_px(py, H); }
     if constexpr (INTERP) {
       q = bilin_setup(px, py, H, W, mw1, mh1);
       raw[0] = ldg_stream16(fb + ((int64_t)q.r0 * W + q.c0) * pixel_bytes);
@@ -172,7 +182,7 @@ __global__ void __launch_bounds__(kGpWarps * 32)
 gather_pool_fwd_cl_kernel(const T* __restrict__ fmap, const int64_t* __restrict__ img,
                           const PIX* __restrict__ pix, const int64_t* __restrict__ aptr,
                           T* __restrict__ out, int64_t* __restrict__ arg, int C, int H, int W,
-                          int64_t Vw, int64_t P, float mw1, float mh1) {
+                          int64_t Vw, int64_t P, float mw1, float mh1, int64_t B) {
   constexpr int VEC = Vec16<T>::N, RPI = 32 / LPR, U = INTERP ? 2 : 4;
   const int lane = threadIdx.x & 31, sg = lane / LPR, lir = lane % LPR;
   const int cv = C / VEC, tiles = (cv + LPR - 1) / LPR;
@@ -194,7 +204,7 @@ gather_pool_fwd_cl_kernel(const T* __restrict__ fmap, const int64_t* __restrict_
       act[u] = act[u] && ck[u] < cv;
       p0[u] = aptr[w[u]];
       n[u] = (int)(aptr[w[u] + 1] - p0[u]);
-      fb[u] = fbase + img[w[u]] * map_bytes + (act[u] ? ck[u] * 16 : 0);
+      fb[u] = fbase + clamp_img(img[w[u]], B) * map_bytes + (act[u] ? ck[u] * 16 : 0);
     }
     PixLoad<T, PIX, INTERP> pl[U];
 #pragma unroll
@@ -242,7 +252,8 @@ template <typename PIX, bool INTERP, int VEC>
 __device__ __forceinline__ void scatter_chunk(float* __restrict__ gmap_b /* image + chunk offset */,
                                               const PIX* __restrict__ pix, int64_t p, int C, int H, int W,
                                               float mw1, float mh1, const float (&g)[VEC]) {
-  const int px = (int)pix[2 * p], py = (int)pix[2 * p + 1];
+  int px = (int)pix[2 * p], py = (int)pix[2 * p + 1];
+  if constexpr (!INTERP) { px = clamp_px(px, W); py = clamp_px(py, H); }
   if constexpr (INTERP) {
     const Bilin q = bilin_setup(px, py, H, W, mw1, mh1);
     const int64_t o[4] = {((int64_t)q.r0 * W + q.c0) * C, ((int64_t)q.r0 * W + q.c1) * C,
@@ -265,7 +276,7 @@ __global__ void __launch_bounds__(kGpWarps * 32)
 gather_pool_bwd_cl_kernel(const T* __restrict__ gout, const int64_t* __restrict__ img,
                           const PIX* __restrict__ pix, const int64_t* __restrict__ aptr,
                           const int64_t* __restrict__ arg, float* __restrict__ gfmap, int C, int H,
-                          int W, int64_t Vw, float mw1, float mh1) {
+                          int W, int64_t Vw, float mw1, float mh1, int64_t B) {
   constexpr int VEC = Vec16<T>::N, RPI = 32 / LPR, U = 4;
   const int lane = threadIdx.x & 31, sg = lane / LPR, lir = lane % LPR;
   const int cv = C / VEC, tiles = (cv + LPR - 1) / LPR;
@@ -285,7 +296,7 @@ gather_pool_bwd_cl_kernel(const T* __restrict__ gout, const int64_t* __restrict_
       act[u] = act[u] && ck[u] < cv;
       p0[u] = aptr[w[u]];
       n[u] = (int)(aptr[w[u] + 1] - p0[u]);
-      b[u] = img[w[u]];
+      b[u] = clamp_img(img[w[u]], B);
       act[u] = act[u] && n[u] > 0;
       if (act[u]) raw[u] = ldg_stream16(reinterpret_cast<const char*>(gout) + (w[u] * C + (int64_t)ck[u] * VEC) * sizeof(T));
     }
@@ -338,14 +349,14 @@ static inline int gp_grid(int64_t total) {
 template <typename T, typename PIX, bool CL, bool INTERP>
 static int gp_fwd_red(const void* fmap, const int64_t* img, const void* pix, const int64_t* aptr,
                       void* out, int64_t* arg, int64_t C, int64_t H, int64_t W, int64_t Vw,
-                      int64_t P, float mw1, float mh1, int reduce, cudaStream_t st) {
+                      int64_t P, float mw1, float mh1, int reduce, cudaStream_t st, int64_t B) {
   if constexpr (CL) {
     if (gp_cl_vec_ok<T>(fmap, out, C, H, W)) {
       const int lpr = gp_cl_lpr<T>(C);
       const int64_t cvv = C / Vec16<T>::N;
       const int64_t items = Vw * ((cvv + lpr - 1) / lpr);
       const int gridv = gp_cl_grid(items, 32 / lpr, INTERP ? 2 : 4);
-#define GP_FV(R, L) gather_pool_fwd_cl_kernel<T, PIX, L, R, INTERP><<<gridv, kGpWarps * 32, 0, st>>>((const T*)fmap, img, (const PIX*)pix, aptr, (T*)out, arg, (int)C, (int)H, (int)W, Vw, P, mw1, mh1)
+#define GP_FV(R, L) gather_pool_fwd_cl_kernel<T, PIX, L, R, INTERP><<<gridv, kGpWarps * 32, 0, st>>>((const T*)fmap, img, (const PIX*)pix, aptr, (T*)out, arg, (int)C, (int)H, (int)W, Vw, P, mw1, mh1, B)
 #define GP_FVL(R) do { if (lpr == 4) GP_FV(R, 4); else if (lpr == 8) GP_FV(R, 8); else if (lpr == 16) GP_FV(R, 16); else GP_FV(R, 32); } while (0)
       switch (reduce) {
         case DVA_SUM: GP_FVL(DVA_SUM); break;
@@ -360,7 +371,7 @@ static int gp_fwd_red(const void* fmap, const int64_t* img, const void* pix, con
     }
   }
   const int grid = gp_grid(Vw * C);
-#define GP_F(R) gather_pool_fwd_kernel<T, PIX, CL, R, INTERP><<<grid, 256, 0, st>>>((const T*)fmap, img, (const PIX*)pix, aptr, (T*)out, arg, C, H, W, Vw, P, mw1, mh1)
+#define GP_F(R) gather_pool_fwd_kernel<T, PIX, CL, R, INTERP><<<grid, 256, 0, st>>>((const T*)fmap, img, (const PIX*)pix, aptr, (T*)out, arg, C, H, W, Vw, P, mw1, mh1, B)
   switch (reduce) {
     case DVA_SUM: GP_F(DVA_SUM); break;
     case DVA_MEAN: GP_F(DVA_MEAN); break;
@@ -375,14 +386,14 @@ static int gp_fwd_red(const void* fmap, const int64_t* img, const void* pix, con
 template <typename T, typename PIX, bool CL, bool INTERP>
 static int gp_bwd_red(const void* gout, const int64_t* img, const void* pix, const int64_t* aptr,
                       const int64_t* arg, float* gfmap, int64_t C, int64_t H, int64_t W,
-                      int64_t Vw, float mw1, float mh1, int reduce, cudaStream_t st) {
+                      int64_t Vw, float mw1, float mh1, int reduce, cudaStream_t st, int64_t B) {
   if constexpr (CL) {
     if (gp_cl_vec_ok<T>(gfmap, gout, C, H, W) && C % 4 == 0) {
       const int lpr = gp_cl_lpr<T>(C);
       const int64_t cvv = C / Vec16<T>::N;
       const int64_t items = Vw * ((cvv + lpr - 1) / lpr);
       const int gridv = gp_cl_grid(items, 32 / lpr, 4);
-#define GP_BV(R, L) gather_pool_bwd_cl_kernel<T, PIX, L, R, INTERP><<<gridv, kGpWarps * 32, 0, st>>>((const T*)gout, img, (const PIX*)pix, aptr, arg, gfmap, (int)C, (int)H, (int)W, Vw, mw1, mh1)
+#define GP_BV(R, L) gather_pool_bwd_cl_kernel<T, PIX, L, R, INTERP><<<gridv, kGpWarps * 32, 0, st>>>((const T*)gout, img, (const PIX*)pix, aptr, arg, gfmap, (int)C, (int)H, (int)W, Vw, mw1, mh1, B)
 #define GP_BVL(R) do { if (lpr == 4) GP_BV(R, 4); else if (lpr == 8) GP_BV(R, 8); else if (lpr == 16) GP_BV(R, 16); else GP_BV(R, 32); } while (0)
       switch (reduce) {
         case DVA_SUM: GP_BVL(DVA_SUM); break;
@@ -397,7 +408,7 @@ static int gp_bwd_red(const void* gout, const int64_t* img, const void* pix, con
     }
   }
   const int grid = gp_grid(Vw * C);
-#define GP_B(R) gather_pool_bwd_kernel<T, PIX, CL, R, INTERP><<<grid, 256, 0, st>>>((const T*)gout, img, (const PIX*)pix, aptr, arg, gfmap, C, H, W, Vw, mw1, mh1)
+#define GP_B(R) gather_pool_bwd_kernel<T, PIX, CL, R, INTERP><<<grid, 256, 0, st>>>((const T*)gout, img, (const PIX*)pix, aptr, arg, gfmap, C, H, W, Vw, mw1, mh1, B)
   switch (reduce) {
     case DVA_SUM: GP_B(DVA_SUM); break;
     case DVA_MEAN: GP_B(DVA_MEAN); break;
@@ -431,15 +442,16 @@ static int gather_pool_fwd_impl(const char* who, const void* fmap, int channels_
                                 int dtype, void* stream) {
   if (B < 0 || C < 0 || H < 0 || W < 0 || Vw < 0 || P < 0) return failf(DVA_EINVAL, "%s: negative size", who);
   if (Vw == 0 || C == 0) return DVA_OK;
+  if (P > 0 && (B < 1 || H < 1 || W < 1)) return failf(DVA_EINVAL, "%s: pixels given but the map is empty", who);
   if (!aptr || !out || !img || (P > 0 && (!fmap || !pix))) return failf(DVA_EINVAL, "%s: null pointer", who);
   if (INTERP && (map_w < 2 || map_h < 2 || H < 1 || W < 1 || H > (1 << 24) || W > (1 << 24)))
     return failf(DVA_EINVAL, "%s: bad map / mapping size", who);
   const float mw1 = (float)(map_w - 1), mh1 = (float)(map_h - 1);
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case DVA_F32: { using T = float; GP_DISPATCH(gp_fwd_red, INTERP, fmap, img, pix, aptr, out, arg, C, H, W, Vw, P, mw1, mh1, reduce, st); }
-    case DVA_BF16: { using T = __nv_bfloat16; GP_DISPATCH(gp_fwd_red, INTERP, fmap, img, pix, aptr, out, arg, C, H, W, Vw, P, mw1, mh1, reduce, st); }
-    case DVA_F16: { using T = __half; GP_DISPATCH(gp_fwd_red, INTERP, fmap, img, pix, aptr, out, arg, C, H, W, Vw, P, mw1, mh1, reduce, st); }
+    case DVA_F32: { using T = float; GP_DISPATCH(gp_fwd_red, INTERP, fmap, img, pix, aptr, out, arg, C, H, W, Vw, P, mw1, mh1, reduce, st, B); }
+    case DVA_BF16: { using T = __nv_bfloat16; GP_DISPATCH(gp_fwd_red, INTERP, fmap, img, pix, aptr, out, arg, C, H, W, Vw, P, mw1, mh1, reduce, st, B); }
+    case DVA_F16: { using T = __half; GP_DISPATCH(gp_fwd_red, INTERP, fmap, img, pix, aptr, out, arg, C, H, W, Vw, P, mw1, mh1, reduce, st, B); }
     default: return failf(DVA_EINVAL, "%s: unknown dtype", who);
   }
 }
@@ -452,6 +464,7 @@ static int gather_pool_bwd_impl(const char* who, const void* grad_out, int chann
                                 int64_t Vw, int64_t P, int reduce, int dtype, void* stream) {
   if (B < 0 || C < 0 || H < 0 || W < 0 || Vw < 0 || P < 0) return failf(DVA_EINVAL, "%s: negative size", who);
   if (Vw == 0 || C == 0 || P == 0) return DVA_OK;
+  if (B < 1 || H < 1 || W < 1) return failf(DVA_EINVAL, "%s: pixels given but the map is empty", who);
   if (!aptr || !grad_out || !img || !pix || !grad_fmap) return failf(DVA_EINVAL, "%s: null pointer", who);
   if ((reduce == DVA_MAX || reduce == DVA_MIN) && !arg) return failf(DVA_EINVAL, "%s: max/min need arg", who);
   if (INTERP && (map_w < 2 || map_h < 2 || H < 1 || W < 1 || H > (1 << 24) || W > (1 << 24)))
@@ -459,9 +472,9 @@ static int gather_pool_bwd_impl(const char* who, const void* grad_out, int chann
   const float mw1 = (float)(map_w - 1), mh1 = (float)(map_h - 1);
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case DVA_F32: { using T = float; GP_DISPATCH(gp_bwd_red, INTERP, grad_out, img, pix, aptr, arg, grad_fmap, C, H, W, Vw, mw1, mh1, reduce, st); }
-    case DVA_BF16: { using T = __nv_bfloat16; GP_DISPATCH(gp_bwd_red, INTERP, grad_out, img, pix, aptr, arg, grad_fmap, C, H, W, Vw, mw1, mh1, reduce, st); }
-    case DVA_F16: { using T = __half; GP_DISPATCH(gp_bwd_red, INTERP, grad_out, img, pix, aptr, arg, grad_fmap, C, H, W, Vw, mw1, mh1, reduce, st); }
+    case DVA_F32: { using T = float; GP_DISPATCH(gp_bwd_red, INTERP, grad_out, img, pix, aptr, arg, grad_fmap, C, H, W, Vw, mw1, mh1, reduce, st, B); }
+    case DVA_BF16: { using T = __nv_bfloat16; GP_DISPATCH(gp_bwd_red, INTERP, grad_out, img, pix, aptr, arg, grad_fmap, C, H, W, Vw, mw1, mh1, reduce, st, B); }
+    case DVA_F16: { using T = __half; GP_DISPATCH(gp_bwd_red, INTERP, grad_out, img, pix, aptr, arg, grad_fmap, C, H, W, Vw, mw1, mh1, reduce, st, B); }
     default: return failf(DVA_EINVAL, "%s: unknown dtype", who);
   }
 }

@@ -16,6 +16,24 @@ template <> struct RedOp<DVA_SUM> { static __device__ __forceinline__ bool bette
 template <> struct RedOp<DVA_MAX> { static __device__ __forceinline__ bool better(float a, float b) { return a > b; } };
 template <> struct RedOp<DVA_MIN> { static __device__ __forceinline__ bool better(float a, float b) { return a < b; } };
 
+// Rows outside [ptr[0], ptr[n_seg]) belong to no segment (torch_scatter accepts such pointers): the
+// element-level outputs (gradients w.r.t. src, gather_csr / softmax results) are 0 there, never
+// uninitialised memory.  Both ranges are empty for a well-formed CSR, so this costs two cached loads.
+template <typename T>
+__device__ __forceinline__ void zero_uncovered_rows(T* __restrict__ dst, const int64_t* __restrict__ ptr,
+                                                    int64_t n_seg, int64_t n_items, int64_t K) {
+  const int64_t head = ptr[0] < n_items ? ptr[0] : n_items;
+  const int64_t tail0 = ptr[n_seg] > head ? ptr[n_seg] : head;
+  const int64_t n_tail = n_items > tail0 ? n_items - tail0 : 0;
+  const int64_t total = (head + n_tail) * K;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / K, c = t - r * K;
+    const int64_t row = r < head ? r : tail0 + (r - head);
+    dst[row * K + c] = Cvt<T>::from_f(0.f);
+  }
+}
+
 // ---- forward -----------------------------------------------------------------------------
 template <typename T, int VEC, int RED>
 __global__ void __launch_bounds__(256)
@@ -67,7 +85,8 @@ template <typename T, int VEC, int RED>
 __global__ void __launch_bounds__(256)
 segment_csr_bwd_kernel(const T* __restrict__ gout, const int64_t* __restrict__ ptr,
                        const int64_t* __restrict__ arg, T* __restrict__ gsrc, int64_t n_seg,
-                       int64_t K) {
+                       int64_t n_items, int64_t K) {
+  zero_uncovered_rows(gsrc, ptr, n_seg, n_items, K);
   const int64_t KV = K / VEC;
   const int64_t total = n_seg * KV;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
@@ -101,7 +120,8 @@ segment_csr_bwd_kernel(const T* __restrict__ gout, const int64_t* __restrict__ p
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
 gather_csr_kernel(const T* __restrict__ src, const int64_t* __restrict__ ptr,
-                  T* __restrict__ out, int64_t n_seg, int64_t K) {
+                  T* __restrict__ out, int64_t n_seg, int64_t n_items, int64_t K) {
+  zero_uncovered_rows(out, ptr, n_seg, n_items, K);
   const int64_t KV = K / VEC;
   const int64_t total = n_seg * KV;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
@@ -119,8 +139,9 @@ gather_csr_kernel(const T* __restrict__ src, const int64_t* __restrict__ ptr,
 template <typename T>
 __global__ void __launch_bounds__(256)
 segment_softmax_fwd_kernel(const T* __restrict__ src, const int64_t* __restrict__ ptr,
-                           T* __restrict__ out, int64_t n_seg, int64_t K, float eps,
+                           T* __restrict__ out, int64_t n_seg, int64_t n_items, int64_t K, float eps,
                            int scaling) {
+  zero_uncovered_rows(out, ptr, n_seg, n_items, K);
   const int64_t total = n_seg * K;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
@@ -143,7 +164,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 segment_softmax_bwd_kernel(const T* __restrict__ out, const T* __restrict__ gout,
                            const int64_t* __restrict__ ptr, T* __restrict__ gsrc,
-                           int64_t n_seg, int64_t K, int scaling) {
+                           int64_t n_seg, int64_t n_items, int64_t K, int scaling) {
+  zero_uncovered_rows(gsrc, ptr, n_seg, n_items, K);
   const int64_t total = n_seg * K;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
@@ -234,14 +256,14 @@ static int seg_fwd_launch(const void* src, const int64_t* ptr, void* out, int64_
 
 template <typename T, int VEC>
 static int seg_bwd_launch(const void* gout, const int64_t* ptr, const int64_t* arg, void* gsrc,
-                          int64_t n_seg, int64_t K, int reduce, cudaStream_t st) {
+                          int64_t n_seg, int64_t n_items, int64_t K, int reduce, cudaStream_t st) {
   const int grid = grid_for(n_seg * (K / VEC));
   const T* g = (const T*)gout; T* o = (T*)gsrc;
   switch (reduce) {
-    case DVA_SUM:  segment_csr_bwd_kernel<T, VEC, DVA_SUM><<<grid, 256, 0, st>>>(g, ptr, arg, o, n_seg, K); break;
-    case DVA_MEAN: segment_csr_bwd_kernel<T, VEC, DVA_MEAN><<<grid, 256, 0, st>>>(g, ptr, arg, o, n_seg, K); break;
-    case DVA_MAX:  segment_csr_bwd_kernel<T, VEC, DVA_MAX><<<grid, 256, 0, st>>>(g, ptr, arg, o, n_seg, K); break;
-    case DVA_MIN:  segment_csr_bwd_kernel<T, VEC, DVA_MIN><<<grid, 256, 0, st>>>(g, ptr, arg, o, n_seg, K); break;
+    case DVA_SUM:  segment_csr_bwd_kernel<T, VEC, DVA_SUM><<<grid, 256, 0, st>>>(g, ptr, arg, o, n_seg, n_items, K); break;
+    case DVA_MEAN: segment_csr_bwd_kernel<T, VEC, DVA_MEAN><<<grid, 256, 0, st>>>(g, ptr, arg, o, n_seg, n_items, K); break;
+    case DVA_MAX:  segment_csr_bwd_kernel<T, VEC, DVA_MAX><<<grid, 256, 0, st>>>(g, ptr, arg, o, n_seg, n_items, K); break;
+    case DVA_MIN:  segment_csr_bwd_kernel<T, VEC, DVA_MIN><<<grid, 256, 0, st>>>(g, ptr, arg, o, n_seg, n_items, K); break;
     default: return fail(DVA_EINVAL, "segment_csr_bwd: unknown reduce");
   }
   return check_launch("segment_csr_bwd");
@@ -254,6 +276,14 @@ static int seg_bwd_launch(const void* gout, const int64_t* ptr, const int64_t* a
     case DVA_F16:  { using T = __half; __VA_ARGS__; } break;                  \
     default: return fail(DVA_EINVAL, "unknown dtype");                        \
   }
+
+// no segment at all: every element-level output row is uncovered
+static int zero_all_rows(void* dst, int64_t n_items, int64_t K, int dtype, cudaStream_t st) {
+  if (!dst) return fail(DVA_EINVAL, "null output");
+  const size_t es = dtype == DVA_F32 ? 4 : 2;
+  const cudaError_t e = cudaMemsetAsync(dst, 0, (size_t)n_items * (size_t)K * es, st);
+  return e == cudaSuccess ? DVA_OK : fail((int)e, "memset failed");
+}
 
 }  // namespace dva
 
@@ -279,15 +309,16 @@ extern "C" int dva_segment_csr_bwd(const void* grad_out, const int64_t* ptr, con
                                    void* grad_src, int64_t n_seg, int64_t n_items, int64_t K,
                                    int reduce, int dtype, void* stream) {
   if (n_seg < 0 || n_items < 0 || K < 0) return fail(DVA_EINVAL, "segment_csr_bwd: negative size");
-  if (n_seg == 0 || K == 0 || n_items == 0) return DVA_OK;
+  if (K == 0 || n_items == 0) return DVA_OK;
+  if (n_seg == 0) return zero_all_rows(grad_src, n_items, K, dtype, (cudaStream_t)stream);
   if (!grad_out || !ptr || !grad_src) return fail(DVA_EINVAL, "segment_csr_bwd: null pointer");
   if ((reduce == DVA_MAX || reduce == DVA_MIN) && !arg)
     return fail(DVA_EINVAL, "segment_csr_bwd: max/min need arg");
   cudaStream_t st = (cudaStream_t)stream;
   DVA_DISPATCH_DTYPE(dtype, {
     if (vec_width<T>(K, grad_out, grad_src) > 1)
-      return seg_bwd_launch<T, Vec16<T>::N>(grad_out, ptr, arg, grad_src, n_seg, K, reduce, st);
-    return seg_bwd_launch<T, 1>(grad_out, ptr, arg, grad_src, n_seg, K, reduce, st);
+      return seg_bwd_launch<T, Vec16<T>::N>(grad_out, ptr, arg, grad_src, n_seg, n_items, K, reduce, st);
+    return seg_bwd_launch<T, 1>(grad_out, ptr, arg, grad_src, n_seg, n_items, K, reduce, st);
   });
   return DVA_OK;
 }
@@ -295,17 +326,18 @@ extern "C" int dva_segment_csr_bwd(const void* grad_out, const int64_t* ptr, con
 extern "C" int dva_gather_csr(const void* src, const int64_t* ptr, void* out, int64_t n_seg,
                               int64_t n_items, int64_t K, int dtype, void* stream) {
   if (n_seg < 0 || n_items < 0 || K < 0) return fail(DVA_EINVAL, "gather_csr: negative size");
-  if (n_seg == 0 || K == 0 || n_items == 0) return DVA_OK;
+  if (K == 0 || n_items == 0) return DVA_OK;
+  if (n_seg == 0) return zero_all_rows(out, n_items, K, dtype, (cudaStream_t)stream);
   if (!src || !ptr || !out) return fail(DVA_EINVAL, "gather_csr: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   DVA_DISPATCH_DTYPE(dtype, {
     if (vec_width<T>(K, src, out) > 1) {
       constexpr int VEC = Vec16<T>::N;
       gather_csr_kernel<T, VEC><<<grid_for(n_seg * (K / VEC)), 256, 0, st>>>(
-          (const T*)src, ptr, (T*)out, n_seg, K);
+          (const T*)src, ptr, (T*)out, n_seg, n_items, K);
     } else {
       gather_csr_kernel<T, 1><<<grid_for(n_seg * K), 256, 0, st>>>((const T*)src, ptr, (T*)out,
-                                                                   n_seg, K);
+                                                                   n_seg, n_items, K);
     }
     return check_launch("gather_csr");
   });
@@ -316,12 +348,13 @@ extern "C" int dva_segment_softmax_csr_fwd(const void* src, const int64_t* ptr, 
                                            int64_t n_seg, int64_t n_items, int64_t K, float eps,
                                            int scaling, int dtype, void* stream) {
   if (n_seg < 0 || n_items < 0 || K < 0) return fail(DVA_EINVAL, "segment_softmax_fwd: negative size");
-  if (n_seg == 0 || K == 0 || n_items == 0) return DVA_OK;
+  if (K == 0 || n_items == 0) return DVA_OK;
+  if (n_seg == 0) return zero_all_rows(out, n_items, K, dtype, (cudaStream_t)stream);
   if (!src || !ptr || !out) return fail(DVA_EINVAL, "segment_softmax_fwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   DVA_DISPATCH_DTYPE(dtype, {
     segment_softmax_fwd_kernel<T><<<grid_for(n_seg * K), 256, 0, st>>>(
-        (const T*)src, ptr, (T*)out, n_seg, K, eps, scaling);
+        (const T*)src, ptr, (T*)out, n_seg, n_items, K, eps, scaling);
     return check_launch("segment_softmax_fwd");
   });
   return DVA_OK;
@@ -332,12 +365,13 @@ extern "C" int dva_segment_softmax_csr_bwd(const void* out, const void* grad_out
                                            int64_t n_items, int64_t K, int scaling, int dtype,
                                            void* stream) {
   if (n_seg < 0 || n_items < 0 || K < 0) return fail(DVA_EINVAL, "segment_softmax_bwd: negative size");
-  if (n_seg == 0 || K == 0 || n_items == 0) return DVA_OK;
+  if (K == 0 || n_items == 0) return DVA_OK;
+  if (n_seg == 0) return zero_all_rows(grad_src, n_items, K, dtype, (cudaStream_t)stream);
   if (!out || !grad_out || !ptr || !grad_src) return fail(DVA_EINVAL, "segment_softmax_bwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   DVA_DISPATCH_DTYPE(dtype, {
     segment_softmax_bwd_kernel<T><<<grid_for(n_seg * K), 256, 0, st>>>(
-        (const T*)out, (const T*)grad_out, ptr, (T*)grad_src, n_seg, K, scaling);
+        (const T*)out, (const T*)grad_out, ptr, (T*)grad_src, n_seg, n_items, K, scaling);
     return check_launch("segment_softmax_bwd");
   });
   return DVA_OK;

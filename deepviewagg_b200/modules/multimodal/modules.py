@@ -241,7 +241,7 @@ class UnimodalBranch(nn.Module):
         fold_gather = isinstance(self.view_pool, (GroupBimodalCSRPool, QKVBimodalCSRPool)) \
             and not self.keep_last_view and not self.view_pool.save_last and x_cat.is_cuda
         if fold_gather:
-            args = (x_3d, x_cat, x_map, csr_idx, idx_sorting)      # gather folded into the kernel
+            args = (x_3d, x_cat, x_map, csr_idx, idx_sorting, True)  # gather folded into the kernel; view_cat_sorting is a permutation
         else:
             x_sorted = x_cat[idx_sorting]
             if self.keep_last_view:

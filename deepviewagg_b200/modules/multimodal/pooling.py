@@ -99,7 +99,8 @@ class HeuristicBimodalCSRPool(nn.Module, _SaveLast):
         return f'mode={self._mode}, feat={self._FEATURES[self._feat]}, save_last={self.save_last}'
 
 
-def _attend(x_mod, compat, csr_idx, num_groups, out_mod, gate, group_scaling, row_index=None):
+def _attend(x_mod, compat, csr_idx, num_groups, out_mod, gate, group_scaling, row_index=None,
+            row_index_is_permutation=False):
     """softmax over views -> weighted sum -> gating. Fused kernel when G is a power of two <= 32,
     otherwise the same chain composed from the unfused CUDA operators.
     Returns (x_pool, attentions, gating or None)."""
@@ -111,7 +112,7 @@ def _attend(x_mod, compat, csr_idx, num_groups, out_mod, gate, group_scaling, ro
             gb = gb if gb is not None else torch.zeros(1, num_groups, device=compat.device)
         x_pool, att, seg_max = ops.view_attention(
             x_mod, compat, csr_idx, num_groups, idx=row_index, gate_weight=gw, gate_bias=gb,
-            group_scaling=group_scaling, idx_is_permutation=row_index is not None)
+            group_scaling=group_scaling, idx_is_permutation=bool(row_index is not None and row_index_is_permutation))
         gating = None
         if gate is not None:
             with torch.no_grad():
@@ -146,7 +147,10 @@ class GroupBimodalCSRPool(nn.Module, _SaveLast):
     concatenation of per-setting view features and row_index the CSR-friendly order
     (ImageData.view_cat_sorting); the gather is folded into the attention kernel instead of the
     [V,C] copy of modules.py:518.  E_mod is row-wise (its BatchNorm statistics are permutation
-    invariant), so E_mod(x)[idx] == E_mod(x[idx]).
+    invariant), so E_mod(x)[idx] == E_mod(x[idx]).  `row_index_is_permutation=True` (set by
+    UnimodalBranch, where view_cat_sorting is a permutation by construction) lets the backward write
+    each x_mod gradient row exactly once; any other row_index (duplicates, subsets) takes the
+    accumulating path.
     """
 
     def __init__(self, in_map=None, in_mod=None, out_mod=None, num_groups=1, use_mod=False,
@@ -168,7 +172,7 @@ class GroupBimodalCSRPool(nn.Module, _SaveLast):
         self.E_score = nn.Linear(nc_inner, num_groups, bias=True)
         self.G = Gating(num_groups, bias=True) if gating else None
 
-    def forward(self, x_main, x_mod, x_map, csr_idx, row_index=None):
+    def forward(self, x_main, x_mod, x_map, csr_idx, row_index=None, row_index_is_permutation=False):
         x_map = self.E_map(x_map, csr_idx)
         x_mod = self.E_mod(x_mod)
         if self.use_mod:
@@ -177,9 +181,10 @@ class GroupBimodalCSRPool(nn.Module, _SaveLast):
         else:
             compatibilities = _biased_linear(self.E_score, x_map)
         x_pool, attentions, gating = _attend(x_mod, compatibilities, csr_idx, self.num_groups,
-                                             self.out_mod, self.G, self.group_scaling, row_index)
+                                             self.out_mod, self.G, self.group_scaling, row_index,
+                                             row_index_is_permutation)
         if self.save_last:
-            self._tap_common(x_map, x_mod, csr_idx)
+            self._tap_common(x_map, x_mod if row_index is None else x_mod[row_index.long()], csr_idx)
             self._last_C, self._last_A = compatibilities, attentions
             if self.G:
                 self._last_G = gating
@@ -225,7 +230,7 @@ class QKVBimodalCSRPool(nn.Module, _SaveLast):
         self.K = nn.Linear(nc_inner, nc_qk * num_groups, bias=True)
         self.G = Gating(num_groups, bias=True) if gating else None
 
-    def forward(self, x_main, x_mod, x_map, csr_idx, row_index=None):
+    def forward(self, x_main, x_mod, x_map, csr_idx, row_index=None, row_index_is_permutation=False):
         x_main = self.E_main(x_main)
         x_map = self.E_map(x_map, csr_idx)
         x_mod = self.E_mod(x_mod)
@@ -245,9 +250,10 @@ class QKVBimodalCSRPool(nn.Module, _SaveLast):
             queries = _biased_linear(self.Q, x_main)  # N x (D x num_groups); never expanded to views
             compatibilities = ops.qk_scores(keys, queries, csr_idx, self.num_groups, self.dim_scaling)
         x_pool, attentions, gating = _attend(x_mod, compatibilities, csr_idx, self.num_groups,
-                                             self.out_mod, self.G, self.group_scaling, row_index)
+                                             self.out_mod, self.G, self.group_scaling, row_index,
+                                             row_index_is_permutation)
         if self.save_last:
-            self._tap_common(x_map, x_mod, csr_idx)
+            self._tap_common(x_map, x_mod if row_index is None else x_mod[row_index.long()], csr_idx)
             self._last_K = keys
             self._last_Q = queries if self.use_mod_q else gather_csr(queries, csr_idx, n_items=keys.shape[0])
             self._last_C, self._last_A = compatibilities, attentions

@@ -6,8 +6,20 @@ libdva_b200.so: CPU tensors or a missing library raise.  Reference citations are
 reference repository root.
 """
 import math
+import os
 
 import torch
+
+# torch.amp integration (SURVEY 8b "Autograd / AMP / recompute"): every autograd.Function's forward is
+# wrapped in torch.amp.custom_fwd and its backward in custom_bwd, so that (a) the backward runs under
+# the autocast state of its forward and (b) the tensor-core projection is computed from fp32 operands
+# (cast_inputs) whatever dtype autocast hands it -- never less precise than the reference's fp16
+# autocast path (models/segmentation/sparseconv3d.py:24).  The feature operators (segment / gather /
+# attention) run in the dtype of their inputs (fp32, bf16 or fp16 storage, fp32 accumulation), which
+# is what torch_scatter does under autocast.
+_fwd = torch.amp.custom_fwd(device_type="cuda")
+_fwd_f32 = torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+_bwd = torch.amp.custom_bwd(device_type="cuda")
 
 from . import _lib
 from ._lib import DTYPE_CODES, REDUCE_CODES, check, dtype_code, ptr, require_cuda, stream_ptr
@@ -36,6 +48,7 @@ def _check_csr(csr_idx, device):
 # --------------------------------------------------------------------------------------------
 class _SegmentCSR(torch.autograd.Function):
     @staticmethod
+    @_fwd
     def forward(ctx, src, csr_idx, reduce):
         require_cuda(src, csr_idx)
         lib = _lib.load()
@@ -59,6 +72,7 @@ class _SegmentCSR(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_bwd
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
         csr_idx, arg = ctx.saved_tensors
@@ -108,6 +122,7 @@ def segment_csr_arg(src, indptr, reduce="max"):
 # --------------------------------------------------------------------------------------------
 class _GatherCSR(torch.autograd.Function):
     @staticmethod
+    @_fwd
     def forward(ctx, src, csr_idx, n_items):
         require_cuda(src, csr_idx)
         lib = _lib.load()
@@ -123,6 +138,7 @@ class _GatherCSR(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_bwd
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
         (csr_idx,) = ctx.saved_tensors
@@ -164,6 +180,7 @@ def segment_gather_csr(src, csr_idx, reduce="sum"):
 # --------------------------------------------------------------------------------------------
 class _SegmentSoftmaxCSR(torch.autograd.Function):
     @staticmethod
+    @_fwd
     def forward(ctx, src, csr_idx, eps, scaling):
         require_cuda(src, csr_idx)
         lib = _lib.load()
@@ -180,6 +197,7 @@ class _SegmentSoftmaxCSR(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_bwd
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
         csr_idx, out = ctx.saved_tensors
@@ -215,6 +233,7 @@ def fused_groups_supported(num_groups):
 
 class _ViewAttention(torch.autograd.Function):
     @staticmethod
+    @_fwd
     def forward(ctx, x, idx, compat, csr_idx, gate_w, gate_b, num_groups, group_scaling, eps,
                 idx_is_permutation):
         require_cuda(x, idx, compat, csr_idx, gate_w, gate_b)
@@ -258,6 +277,7 @@ class _ViewAttention(torch.autograd.Function):
         return out, att, seg_max
 
     @staticmethod
+    @_bwd
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out, _ga, _gm):
         x, idx, compat, csr_idx, gw, gb, seg_max, seg_den, seg_arg = ctx.saved_tensors
@@ -311,6 +331,7 @@ def view_attention(x, compat, csr_idx, num_groups, idx=None, gate_weight=None, g
 # --------------------------------------------------------------------------------------------
 class _QKScores(torch.autograd.Function):
     @staticmethod
+    @_fwd
     def forward(ctx, keys, queries, csr_idx, num_groups, scale):
         require_cuda(keys, queries, csr_idx)
         lib = _lib.load()
@@ -329,6 +350,7 @@ class _QKScores(torch.autograd.Function):
         return compat
 
     @staticmethod
+    @_bwd
     @torch.autograd.function.once_differentiable
     def backward(ctx, gcompat):
         k32, q32, csr_idx = ctx.saved_tensors
@@ -354,6 +376,7 @@ def qk_scores(keys, queries, csr_idx, num_groups, dim_scaling=True):
 # --------------------------------------------------------------------------------------------
 class _HeuristicPool(torch.autograd.Function):
     @staticmethod
+    @_fwd
     def forward(ctx, x_mod, x_map, csr_idx, feat, use_max):
         require_cuda(x_mod, x_map, csr_idx)
         lib = _lib.load()
@@ -372,6 +395,7 @@ class _HeuristicPool(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_bwd
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
         (arg,) = ctx.saved_tensors
@@ -402,8 +426,31 @@ def _transpose_last2(t, B, R, S):
 _NCHW_TRANSPOSE_SHARE = 0.25
 
 
+_INDEX_CHECKS = {"on": os.environ.get("DVA_CHECK_INDICES", "0") not in ("", "0")}
+
+
+def set_index_checks(on):
+    """Validate pixel / image indices of every gather_pool / interp_pool call on the host (one
+    device->host read per call) and raise IndexError like the reference's
+    `x[feature_map_indexing]` (image.py:1285).  Off by default: the kernels clamp out-of-range
+    indices into the map (memory-safe, no synchronisation).  Also switched on by DVA_CHECK_INDICES=1."""
+    _INDEX_CHECKS["on"] = bool(on)
+
+
+def _validate_gather_indices(images, pixels, B, W, H):
+    if pixels.numel() == 0:
+        return
+    lo = torch.stack([pixels[:, 0].min(), pixels[:, 1].min(), images.min()]).tolist()
+    hi = torch.stack([pixels[:, 0].max(), pixels[:, 1].max(), images.max()]).tolist()
+    if lo[0] < 0 or lo[1] < 0 or lo[2] < 0 or hi[0] >= W or hi[1] >= H or hi[2] >= B:
+        raise IndexError(f"mapping out of bounds for feature maps [B={B}, H={H}, W={W}]: pixels x in "
+                         f"[{lo[0]}, {hi[0]}], y in [{lo[1]}, {hi[1]}], image ids in [{lo[2]}, {hi[2]}] "
+                         f"(stale or mis-scaled mapping?)")
+
+
 class _GatherPool(torch.autograd.Function):
     @staticmethod
+    @_fwd
     def forward(ctx, fmap, images, pixels, atomic_ptr, reduce, channels_last, mapping_size):
         require_cuda(fmap, images, pixels, atomic_ptr)
         lib = _lib.load()
@@ -425,6 +472,11 @@ class _GatherPool(torch.autograd.Function):
         pixels = pixels.contiguous()
         atomic_ptr = _check_csr(atomic_ptr, fmap.device)
         Vw, P, code = atomic_ptr.numel() - 1, pixels.shape[0], REDUCE_CODES[reduce]
+        if images.numel() != Vw:
+            raise ValueError("images must hold one image id per view (atomic_ptr.numel() - 1)")
+        if _INDEX_CHECKS["on"]:
+            lim = (W, H) if mapping_size is None else mapping_size
+            _validate_gather_indices(images, pixels.long(), B, int(lim[0]), int(lim[1]))
         out = torch.empty((Vw, C), dtype=fmap.dtype, device=fmap.device)
         arg = torch.empty((Vw, C), dtype=torch.int64, device=fmap.device) if code in (2, 3) else None
         head = (ptr(fmap), int(channels_last), ptr(images), ptr(pixels), int(pixels.dtype == torch.int16),
@@ -441,6 +493,7 @@ class _GatherPool(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_bwd
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
         images, pixels, atomic_ptr, arg = ctx.saved_tensors
@@ -489,6 +542,7 @@ def sparse_interpolation_pixels(fmap, images_per_pixel, pixels, mapping_size, ch
 # --------------------------------------------------------------------------------------------
 class _BNAct(torch.autograd.Function):
     @staticmethod
+    @_fwd
     def forward(ctx, z, weight, bias, running_mean, running_var, training, momentum, eps, slope):
         require_cuda(z, weight, bias, running_mean, running_var)
         lib = _lib.load()
@@ -510,16 +564,31 @@ class _BNAct(torch.autograd.Function):
         rv = running_var if (training and running_var is not None) else None
         if not training:
             rm, rv = running_mean, running_var
+        # the training kernel updates the running buffers IN PLACE through raw float pointers
+        stage = []
+        for name, buf in (("running_mean", rm), ("running_var", rv)):
+            if buf is not None and (buf.dtype != torch.float32 or not buf.is_contiguous()):
+                if not training:
+                    raise TypeError(f"{name} must be a contiguous float32 buffer in eval mode")
+                stage.append((name, buf, buf.float().contiguous()))   # e.g. a module converted with .half()
+        for name, _, tmp in stage:
+            if name == "running_mean":
+                rm = tmp
+            else:
+                rv = tmp
         with torch.cuda.device(dev):
             check(lib.dva_bn_act_fwd(ptr(z), ptr(gamma), ptr(beta), ptr(rm), ptr(rv), ptr(mean), ptr(invstd), ptr(y),
                                      R, C, float(eps), float(momentum), float(slope), int(bool(training)),
                                      dtype_code(z), ptr(ws), ws_bytes, stream_ptr()), "dva_bn_act_fwd")
+        for _, buf, tmp in stage:
+            buf.copy_(tmp)
         ctx.cfg = (R, C, float(slope), bool(training), weight is not None, bias is not None,
                    weight.dtype if weight is not None else None)
         ctx.save_for_backward(z, gamma, beta, mean, invstd)
         return y
 
     @staticmethod
+    @_bwd
     @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
         z, gamma, beta, mean, invstd = ctx.saved_tensors
@@ -588,28 +657,29 @@ def _tc_gemm(a, b, layout, n_out):
 
 
 def tc_gemm_supported(x, weight):
-    """fp32 [rows, K] x [N, K]: K and N both <= 64 (skinny exact-fp32 kernels, any K / N) or both
-    multiples of 4 (tcgen05 kernels, 16-byte TMA rows)."""
-    if not (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and x.dim() == 2
-            and x.shape[0] > 0):
-        return False
-    K, N = x.shape[1], weight.shape[0]
-    return (K <= 64 and N <= 64) or (K % 4 == 0 and N % 4 == 0)
+    """True for 2-D CUDA floating-point inputs with at least one row: every such projection runs on
+    this library's kernels (K, N <= 64: skinny kernels, any K / N; otherwise the tcgen05 kernels, whose
+    16-byte TMA rows need K and N to be multiples of 4 -- other widths are zero-padded by `linear`)."""
+    return bool(x.is_cuda and weight.is_cuda and x.dim() == 2 and x.shape[0] > 0
+                and x.is_floating_point() and weight.is_floating_point())
 
 
 class _Linear(torch.autograd.Function):
     @staticmethod
+    @_fwd_f32
     def forward(ctx, x, weight):
         require_cuda(x, weight)
-        x, w = x.contiguous(), weight.contiguous()
+        x, w = x.float().contiguous(), weight.float().contiguous()
         ctx.save_for_backward(x, w)
+        ctx.dtypes = (x.dtype, weight.dtype)
         return _tc_gemm(x, w, 0, w.shape[0])
 
     @staticmethod
+    @_bwd
     @torch.autograd.function.once_differentiable
     def backward(ctx, gz):
         x, w = ctx.saved_tensors
-        gz = gz.contiguous()
+        gz = gz.float().contiguous()
         gx = _tc_gemm(gz, w, 1, w.shape[1]) if ctx.needs_input_grad[0] else None
         # dW = dZ^T X: [out,in] result reduced over all rows -- stream-K split over the SMs
         gw = _tc_gemm(gz, x, 2, x.shape[1]) if ctx.needs_input_grad[1] else None
@@ -617,8 +687,23 @@ class _Linear(torch.autograd.Function):
 
 
 def linear(x, weight):
-    """x @ weight.T for a bias-free nn.Linear weight [out, in] (base_modules.py:42) on the tensor
-    cores; shapes the TMA path cannot take (K or N not a multiple of 4, non-fp32) use F.linear."""
+    """x @ weight.T for a bias-free nn.Linear weight [out, in] (base_modules.py:42), always on this
+    library's kernels, computed from fp32 operands (also under autocast).  Wide layers whose K or N is
+    not a multiple of 4 are zero-padded to the next multiple (exact: the padding contributes 0)."""
     if not tc_gemm_supported(x, weight):
-        return torch.nn.functional.linear(x, weight)
-    return _Linear.apply(x, weight)
+        raise RuntimeError("ops.linear needs 2-D CUDA floating-point operands with at least one row "
+                           "(no CPU / library fallback)")
+    out_dtype = x.dtype if not torch.is_autocast_enabled("cuda") else torch.float32
+    K, N = x.shape[1], weight.shape[0]
+    if not (K <= 64 and N <= 64):
+        pk, pn = (-K) % 4, (-N) % 4
+        if pk:
+            x = torch.nn.functional.pad(x, (0, pk))
+            weight = torch.nn.functional.pad(weight, (0, pk))
+        if pn:
+            weight = torch.nn.functional.pad(weight, (0, 0, 0, pn))
+        z = _Linear.apply(x, weight)
+        z = z[:, :N] if pn else z
+    else:
+        z = _Linear.apply(x, weight)
+    return z if z.dtype == out_dtype or out_dtype not in (torch.float16, torch.bfloat16) else z.to(out_dtype)
