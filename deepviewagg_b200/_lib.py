@@ -57,8 +57,15 @@ SIGNATURES = {
                             _vp, _vp, _vp]),
     "dva_neighborhood_features": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _f64, _i32, _i32, _vp,
                                          _i64, _i64, _vp]),
+    "dva_mapping_build_workspace_bytes": (_sz, [_i64, _i64]),
+    "dva_mapping_build": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
+                                 _vp, _vp, _sz, _vp]),
+    "dva_view_cat_sorting": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "dva_linear_gemm_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32, _i32]),
     "dva_linear_gemm": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _sz, _vp]),
+    "dva_linear_bnstats_supported": (_i32, [_i64, _i64, _i64]),
+    "dva_linear_bnstats_workspace_bytes": (_sz, [_i64, _i64]),
+    "dva_linear_bnstats_fwd": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dva_bn_workspace_bytes": (_sz, [_i64, _i64]),
     "dva_bn_act_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32, _i32, _i32,
                               _vp, _sz, _vp]),

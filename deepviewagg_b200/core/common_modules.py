@@ -45,9 +45,9 @@ class MLPLayer(nn.Sequential):
             return super().forward(x)
         slope = act.negative_slope if isinstance(act, nn.LeakyReLU) else (0.0 if isinstance(act, nn.ReLU) else 1.0)
         from .. import ops
-        z = ops.linear(x, lin.weight)
-        if lin.bias is not None:
-            z = z + lin.bias
+        if lin.bias is None:      # every MLP of the pools (bias=False): statistics fused into the GEMM when possible
+            return ops.linear_bn_act(x, lin.weight, bn.batch_norm, negative_slope=slope)
+        z = ops.linear(x, lin.weight) + lin.bias
         return ops.batch_norm_act(z, bn.batch_norm, negative_slope=slope)
 
 

@@ -18,9 +18,56 @@ from typing import List
 import numpy as np
 import torch
 
-from ... import ops
+from ... import _lib, ops
 from ...utils.multimodal import composite_key, lexargsort, lexargunique, lexunique, tensor_idx
 from .csr import CSRBatch, CSRData, pointers_from_sorted
+
+_PIX_CODES = {torch.int16: 0, torch.int32: 1, torch.int64: 2}
+
+
+def _native_mapping_build(point_ids, image_ids, pixels, features, num_points, feat_row=None, feat_on=None,
+                          dedupe=False):
+    """dva_mapping_build on CUDA tensors: bucket the items by point (counting sort), order every
+    point's items with a warp rank sort on (image[, x, y], source index), cut views / dedupe pixels,
+    average the view features -- all on the current stream, ONE device->host read (the output sizes).
+    Returns an ImageMapping."""
+    lib = _lib.load()
+    dev = point_ids.device
+    n = int(point_ids.shape[0])
+    if pixels.dtype not in _PIX_CODES:
+        pixels = pixels.long()
+    pixels = pixels.contiguous()
+    point_ids, image_ids = point_ids.long().contiguous(), image_ids.long().contiguous()
+    F = 0 if features is None else int(features.shape[1])
+    if F > 16:
+        raise NotImplementedError("mapping features wider than 16 columns")
+    feat = features.float().contiguous() if features is not None else None
+    view_ptr = torch.empty(num_points + 1, dtype=torch.long, device=dev)
+    images_out = torch.empty(n, dtype=torch.long, device=dev)
+    atomic_ptr = torch.empty(n + 1, dtype=torch.long, device=dev)
+    pixels_out = torch.empty_like(pixels)
+    feat_out = torch.empty((n, F), dtype=torch.float32, device=dev) if feat is not None else None
+    counts = torch.empty(3, dtype=torch.long, device=dev)
+    ws_bytes = int(lib.dva_mapping_build_workspace_bytes(n, num_points))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    if feat_on is not None:
+        feat_on = feat_on.to(torch.uint8).contiguous()
+    if feat_row is not None:
+        feat_row = feat_row.long().contiguous()
+    with torch.cuda.device(dev):
+        _lib.check(lib.dva_mapping_build(
+            _lib.ptr(point_ids), _lib.ptr(image_ids), _lib.ptr(pixels), _PIX_CODES[pixels.dtype], _lib.ptr(feat),
+            _lib.ptr(feat_row), _lib.ptr(feat_on), F, n, int(num_points), int(bool(dedupe)), _lib.ptr(view_ptr),
+            _lib.ptr(images_out), _lib.ptr(atomic_ptr), _lib.ptr(pixels_out), _lib.ptr(feat_out), None,
+            _lib.ptr(counts), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()), "dva_mapping_build")
+    V, P, status = counts.tolist()                           # the only synchronisation
+    if status != 0:
+        raise IndexError("from_dense: point ids outside [0, num_points)")
+    atomic = CSRData(atomic_ptr[:V + 1], pixels_out[:P], dense=False)
+    if feat is None:
+        return ImageMapping(view_ptr, images_out[:V], atomic, dense=False, is_index_value=[True, False])
+    return ImageMapping(view_ptr, images_out[:V], atomic, feat_out[:V].to(features.dtype), dense=False,
+                        is_index_value=[True, False, False])
 
 
 # ------------------------------------------------------------------------------------------------
@@ -79,6 +126,9 @@ class ImageMapping(CSRData):
         assert point_ids.ndim == 1 and point_ids.shape == image_ids.shape
         assert point_ids.shape[0] == pixels.shape[0]
         assert features is None or point_ids.shape[0] == features.shape[0]
+        if point_ids.is_cuda and num_points is not None and (features is None or features.shape[1] <= 16):
+            # native builder: no sort over all items, no intermediate tensors, one host read
+            return _native_mapping_build(point_ids, image_ids, pixels, features, int(num_points))
         order = lexargsort(point_ids, image_ids)
         image_ids, point_ids, pixels = image_ids[order], point_ids[order], pixels[order]
         if features is not None:
@@ -96,6 +146,12 @@ class ImageMapping(CSRData):
             return ImageMapping(pointers, image_ids, atomic, dense=False, is_index_value=[True, False])
         return ImageMapping(pointers, image_ids, atomic, features, dense=False,
                             is_index_value=[True, False, False])
+
+    def is_cuda_native(self):
+        """True when the native re-indexing kernels apply (CUDA tensors, <= 16 feature columns, pixel
+        coordinates that fit the 16-bit sort key)."""
+        return (self.pointers.is_cuda and (not self.has_features or self.features.shape[1] <= 16)
+                and self.pixels.dtype in (torch.int16, torch.int32, torch.int64))
 
     def debug(self):
         super().debug()
@@ -272,6 +328,23 @@ class ImageMapping(CSRData):
         if not idx.shape[0] == self.num_groups > 0:
             return self.clone()
         n_out = int(idx.max().item()) + 1
+        if self.is_cuda_native():
+            present = torch.zeros(n_out, dtype=torch.bool, device=self.device)
+            present[idx] = True
+            if not bool(present.all()):              # every output voxel must appear (image.py:2220)
+                return self.clone()
+            # native path: items = pixels, bucketed by the merged point; a merged view's feature is the mean
+            # over its SOURCE VIEWS (image.py:2233-2247), i.e. over the first pixel of every source view
+            ap = self.values[1].pointers
+            V, P = self.num_items, int(self.pixels.shape[0])
+            view_points = idx.repeat_interleave(_counts(self.pointers), output_size=V)
+            pcount = _counts(ap)
+            view_of_pixel = torch.arange(V, device=self.device).repeat_interleave(pcount, output_size=P)
+            first = torch.zeros(P, dtype=torch.uint8, device=self.device)
+            first[ap[:-1][pcount > 0]] = 1
+            return _native_mapping_build(view_points[view_of_pixel], self.images[view_of_pixel], self.pixels,
+                                         self.features if self.has_features else None, n_out,
+                                         feat_row=view_of_pixel, feat_on=first, dedupe=True)
         if idx.unique().numel() != n_out:
             return self.clone()
         view_points = _expand(idx, self.pointers)
@@ -625,9 +698,32 @@ class ImageData:
     def view_cat_sorting(self):
         """Permutation that puts the concatenated per-setting views in point order
         (image.py:1549-1574); stable, i.e. ties keep the (setting, view) order."""
+        if self.device.type == 'cuda' and self.num_settings > 0:
+            return self._view_cat_native()[0]
         dense = torch.cat([
             _expand(torch.arange(im.num_points, device=self.device), im.view_csr_indexing) for im in self])
         return torch.sort(dense, stable=True).indices
+
+    def _view_cat_native(self):
+        """(sorting, csr_cat) in closed form (dva_view_cat_sorting): every setting's views are already
+        grouped by point, so a view's slot in the merged order is a sum of pointers -- no sort."""
+        lib = _lib.load()
+        ptrs = [im.view_csr_indexing.contiguous() for im in self]
+        N = int(ptrs[0].numel()) - 1
+        sizes = [int(im.mappings.images.shape[0]) if im.mappings is not None else 0 for im in self]
+        bases, tot = [], 0
+        for sz in sizes:
+            bases.append(tot)
+            tot += sz
+        dev = self.device
+        table = torch.tensor([p.data_ptr() for p in ptrs] + bases, dtype=torch.long).to(dev)
+        sorting = torch.empty(tot, dtype=torch.long, device=dev)
+        csr_cat = torch.empty(N + 1, dtype=torch.long, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.dva_view_cat_sorting(_lib.ptr(table), table.data_ptr() + 8 * len(ptrs), len(ptrs), N,
+                                                _lib.ptr(sorting), _lib.ptr(csr_cat), _lib.stream_ptr()),
+                       "dva_view_cat_sorting")
+        return sorting, csr_cat
 
     @property
     def view_cat_csr_indexing(self):

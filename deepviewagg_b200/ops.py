@@ -543,7 +543,8 @@ def sparse_interpolation_pixels(fmap, images_per_pixel, pixels, mapping_size, ch
 class _BNAct(torch.autograd.Function):
     @staticmethod
     @_fwd
-    def forward(ctx, z, weight, bias, running_mean, running_var, training, momentum, eps, slope):
+    def forward(ctx, z, weight, bias, running_mean, running_var, training, momentum, eps, slope,
+                pre_mean=None, pre_invstd=None):
         require_cuda(z, weight, bias, running_mean, running_var)
         lib = _lib.load()
         z = z.contiguous()
@@ -552,7 +553,12 @@ class _BNAct(torch.autograd.Function):
         gamma = weight.detach().float().contiguous() if weight is not None else None
         beta = bias.detach().float().contiguous() if bias is not None else None
         y = torch.empty_like(z)
-        if training:
+        # batch statistics already taken in the producing GEMM's epilogue (ops.linear_bn_act): apply only;
+        # the backward still differentiates through the batch statistics (ctx keeps training = True)
+        have_stats = training and pre_mean is not None
+        if have_stats:
+            mean, invstd = pre_mean, pre_invstd
+        elif training:
             mean = torch.empty(C, dtype=torch.float32, device=dev)
             invstd = torch.empty(C, dtype=torch.float32, device=dev)
         else:
@@ -564,9 +570,14 @@ class _BNAct(torch.autograd.Function):
         rv = running_var if (training and running_var is not None) else None
         if not training:
             rm, rv = running_mean, running_var
+        kernel_training = training and not have_stats
+        if have_stats:
+            rm = rv = mean                     # eval-style call: the kernel only reads mean / invstd
         # the training kernel updates the running buffers IN PLACE through raw float pointers
         stage = []
         for name, buf in (("running_mean", rm), ("running_var", rv)):
+            if have_stats:
+                break
             if buf is not None and (buf.dtype != torch.float32 or not buf.is_contiguous()):
                 if not training:
                     raise TypeError(f"{name} must be a contiguous float32 buffer in eval mode")
@@ -578,7 +589,7 @@ class _BNAct(torch.autograd.Function):
                 rv = tmp
         with torch.cuda.device(dev):
             check(lib.dva_bn_act_fwd(ptr(z), ptr(gamma), ptr(beta), ptr(rm), ptr(rv), ptr(mean), ptr(invstd), ptr(y),
-                                     R, C, float(eps), float(momentum), float(slope), int(bool(training)),
+                                     R, C, float(eps), float(momentum), float(slope), int(bool(kernel_training)),
                                      dtype_code(z), ptr(ws), ws_bytes, stream_ptr()), "dva_bn_act_fwd")
         for _, buf, tmp in stage:
             buf.copy_(tmp)
@@ -605,7 +616,7 @@ class _BNAct(torch.autograd.Function):
                                      stream_ptr()), "dva_bn_act_bwd")
         gw = sums[1].to(wdt) if has_w else None
         gb = sums[0].to(wdt) if has_b else None
-        return dz, gw, gb, None, None, None, None, None, None
+        return dz, gw, gb, None, None, None, None, None, None, None, None
 
 
 def batch_norm_act(z, bn, negative_slope=1.0):
@@ -627,11 +638,12 @@ def batch_norm_act(z, bn, negative_slope=1.0):
 # --------------------------------------------------------------------------------------------
 # dense projection of the MLP layers on tcgen05 tensor cores (base_modules.py:42)
 # --------------------------------------------------------------------------------------------
-_GEMM_PRECISION = {"mode": 0}   # 0: fast-FP32 (9 x BF16, parity mode), 1: TF32
+_GEMM_PRECISION = {"mode": 0}
 
 
 def set_gemm_precision(mode):
-    """'fp32' (default; 9xBF16 split products, fp32-grade accuracy) or 'tf32'."""
+    """Kept for API stability: 'fp32' or 'tf32'.  Every projection kernel is 3xTF32 (fp32-grade
+    accuracy) since round 2, so both modes run the same code."""
     _GEMM_PRECISION["mode"] = {"fp32": 0, "tf32": 1}[mode]
 
 
@@ -684,6 +696,76 @@ class _Linear(torch.autograd.Function):
         # dW = dZ^T X: [out,in] result reduced over all rows -- stream-K split over the SMs
         gw = _tc_gemm(gz, x, 2, x.shape[1]) if ctx.needs_input_grad[1] else None
         return gx, gw
+
+
+class _LinearStats(torch.autograd.Function):
+    """z = x @ weight.T with the BatchNorm batch statistics of z's columns taken in the GEMM epilogue
+    (dva_linear_bnstats_fwd): returns (z, mean, invstd); running buffers are updated in place."""
+
+    @staticmethod
+    @_fwd_f32
+    def forward(ctx, x, weight, running_mean, running_var, momentum, eps):
+        require_cuda(x, weight)
+        lib = _lib.load()
+        x, w = x.float().contiguous(), weight.float().contiguous()
+        M, K = x.shape
+        N = w.shape[0]
+        z = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        mean = torch.empty(N, dtype=torch.float32, device=x.device)
+        invstd = torch.empty(N, dtype=torch.float32, device=x.device)
+        stage = []
+        rm, rv = running_mean, running_var
+        for name, buf in (("m", rm), ("v", rv)):
+            if buf is not None and (buf.dtype != torch.float32 or not buf.is_contiguous()):
+                stage.append((name, buf, buf.float().contiguous()))
+        for name, _, tmp in stage:
+            if name == "m":
+                rm = tmp
+            else:
+                rv = tmp
+        ws_bytes = int(lib.dva_linear_bnstats_workspace_bytes(N, K))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.dva_linear_bnstats_fwd(ptr(x), ptr(w), ptr(z), M, N, K, float(eps), float(momentum), ptr(mean),
+                                             ptr(invstd), ptr(rm), ptr(rv), ptr(ws), ws_bytes, stream_ptr()),
+                  "dva_linear_bnstats_fwd")
+        for _, buf, tmp in stage:
+            buf.copy_(tmp)
+        ctx.save_for_backward(x, w)
+        ctx.mark_non_differentiable(mean, invstd)
+        return z, mean, invstd
+
+    @staticmethod
+    @_bwd
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gz, _gm, _gi):
+        x, w = ctx.saved_tensors
+        gz = gz.float().contiguous()
+        gx = _tc_gemm(gz, w, 1, w.shape[1]) if ctx.needs_input_grad[0] else None
+        gw = _tc_gemm(gz, x, 2, x.shape[1]) if ctx.needs_input_grad[1] else None
+        return gx, gw, None, None, None, None
+
+
+def linear_bn_act(x, weight, bn, negative_slope=1.0):
+    """act(BatchNorm1d(x @ weight.T)): one MLP layer of the pools (base_modules.py:38-48).  In training,
+    when the layer is wide enough for the tcgen05 kernel and has at most 128 output channels, the batch
+    statistics come out of the GEMM epilogue (2 passes over the activations instead of 3); otherwise
+    linear() followed by batch_norm_act()."""
+    lib = _lib.load()
+    M, K = x.shape
+    N = weight.shape[0]
+    training = bn.training or (bn.running_mean is None and bn.running_var is None)
+    if not (training and x.is_cuda and M > 0 and K % 4 == 0 and lib.dva_linear_bnstats_supported(M, N, K)):
+        return batch_norm_act(linear(x, weight), bn, negative_slope=negative_slope)
+    momentum = 0.0 if bn.momentum is None else bn.momentum
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        if bn.momentum is None:
+            momentum = 1.0 / float(bn.num_batches_tracked)
+    rm = bn.running_mean if bn.track_running_stats else None
+    rv = bn.running_var if bn.track_running_stats else None
+    z, mean, invstd = _LinearStats.apply(x, weight, rm, rv, momentum, bn.eps)
+    return _BNAct.apply(z, bn.weight, bn.bias, rm, rv, True, momentum, bn.eps, negative_slope, mean, invstd)
 
 
 def linear(x, weight):

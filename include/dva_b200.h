@@ -216,19 +216,38 @@ int dva_neighborhood_features(const float* xyz, const int64_t* neighbors, int km
  *   layout 0: D[M,N] = A[M,K] . B[N,K]^T   (forward,  B = weight [out,in])
  *   layout 1: D[M,N] = A[M,K] . B[K,N]     (backward, dX = dZ . weight)
  *   layout 2: D[N,K] = A[M,N]^T . B[M,K]   (backward, dW = dZ^T . X; stream-K over the M rows)
- *   precision 0: fast-FP32 (9 x BF16 split products, fp32-grade accuracy); 1: TF32.
  *   fp32 row-major operands.  Two kernel families behind the one entry point:
  *     N <= 64 and K <= 64 (any values; every MLP of the map encoders, pooling.py:645-656): "skinny"
  *       kernels -- weights in shared memory, 128-row tiles double-buffered by cp.async, coalesced
  *       16-byte global traffic, 3xTF32 split operands on mma.sync (fp32-grade accuracy, ~1e-6), dW
- *       as per-CTA partials reduced in a fixed order (deterministic); precision is ignored;
- *     otherwise the tcgen05 kernels: operands 16-byte aligned, N % 4 == 0 and K % 4 == 0 (else
- *       DVA_EUNSUPPORTED: the host falls back to a library GEMM).
+ *       as per-CTA partials reduced in a fixed order (deterministic);
+ *     otherwise the hand-written tcgen05 kernels of csrc/tc_gemm.cu (TMA-fed tcgen05.mma kind::tf32,
+ *       TMEM accumulators, 3xTF32 split operands: ~1e-6 of the result's max against fp64; dW as
+ *       per-CTA partial tiles reduced in a fixed order): operands 16-byte aligned, N % 4 == 0 and
+ *       K % 4 == 0 (else DVA_EUNSUPPORTED; ops.linear zero-pads such widths).
+ *   `precision` is accepted for ABI stability (0 or 1) and ignored: every path is fp32-grade.
  *   workspace: dva_linear_gemm_workspace_bytes().
  * ------------------------------------------------------------------------------------------ */
 size_t dva_linear_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int layout, int precision);
 int dva_linear_gemm(const float* A, const float* B, float* D, int64_t M, int64_t N, int64_t K, int layout,
                     int precision, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * P9  Linear with the BatchNorm batch statistics taken in the GEMM epilogue
+ *   replaces base_modules.py:42-44 (nn.Linear(bias=False) followed by the statistics half of
+ *   FastBatchNorm1d) for the wide layers (E_mod, E_mix, E_main): D[M,n_out] = X[M,k_red] . W[n_out,k_red]^T
+ *   by the tcgen05 rows kernel, whose epilogue threads each own one output column and accumulate its
+ *   shifted sum / sum of squares while storing; a one-warp-per-column kernel combines the per-CTA
+ *   partials in fp64 (fixed order) into mean / invstd [n_out] (biased variance) and updates the running
+ *   buffers (momentum, unbiased variance) like nn.BatchNorm1d.  The apply half is dva_bn_act_fwd with
+ *   training = 0 on these mean / invstd.  supported(): n_out <= 128, n_out % 4 == 0, k_red % 4 == 0 and
+ *   not a skinny shape (n_out <= 64 and k_red <= 64); else DVA_EUNSUPPORTED.
+ * ------------------------------------------------------------------------------------------ */
+int dva_linear_bnstats_supported(int64_t M, int64_t n_out, int64_t k_red);
+size_t dva_linear_bnstats_workspace_bytes(int64_t n_out, int64_t k_red);
+int dva_linear_bnstats_fwd(const float* X, const float* W, float* D, int64_t M, int64_t n_out, int64_t k_red,
+                           float eps, float momentum, float* mean, float* invstd, float* running_mean,
+                           float* running_var, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * P9  fused BatchNorm1d (+ LeakyReLU) of an MLP layer
@@ -304,6 +323,31 @@ int dva_project_equirectangular(const float* xyz, const float* img_pose, float* 
 int dva_project_camera(const float* xyz, const float* cam, int camera, float* dist, double* x_proj,
                        double* y_proj, uint8_t* keep, int64_t n, int64_t W, int64_t H,
                        int64_t crop_top, int64_t crop_bottom, float r_min, float r_max, void* stream);
+
+/* I1 / I4 / I6  native construction of the point -> view -> pixel CSR (csrc/mapping_build.cu)
+ *   replaces ImageMapping.from_dense image.py:1728-1795 (lexargsort + unique + cumsum chains) and the
+ *   dense expansion / lexargunique / scatter_mean / from_dense sequence of select_points('merge')
+ *   image.py:2211-2273.  Items i = 0..n-1: (point_ids[i] in [0, num_points), image_ids[i], pixels[i] = (x, y)
+ *   as int16 / int32 / int64 pairs: pix_code 0 / 1 / 2).  Items are bucketed by point (histogram, scan,
+ *   scatter) and every point's items ordered by (image, source index) -- or, with dedupe_pixels,
+ *   by (image, x, y, source index; 0 <= x, y < 65536) dropping repeated (image, x, y).  Outputs, all
+ *   preallocated by the caller with n (resp. n + 1) rows: view_ptr [num_points + 1], images_out [V],
+ *   atomic_ptr [V + 1], pixels_out [P, 2] (same integer type), feat_out [V, F] = mean of
+ *   feat[feat_row ? feat_row[i] : i] over the view's items with feat_on[i] != 0 (nullable: all), F <= 16;
+ *   order_out [P] (nullable) = source item of every kept pixel; counts [3] (device) = V, P, status
+ *   (status bit 0: a point id was out of range; such items are skipped).  Deterministic = the result of a
+ *   stable lexicographic sort.  Nothing is read back: the caller reads `counts` once to slice the outputs.
+ *   dva_view_cat_sorting: ImageData.view_cat_sorting / view_cat_csr_indexing image.py:1549-1588 for S
+ *   settings over the same N points in closed form (no argsort): ptrs = device array of S device pointers
+ *   to the settings' view pointers [N + 1], bases[s] = views of the settings before s. */
+size_t dva_mapping_build_workspace_bytes(int64_t n_items, int64_t num_points);
+int dva_mapping_build(const int64_t* point_ids, const int64_t* image_ids, const void* pixels, int pix_code,
+                      const float* feat, const int64_t* feat_row, const uint8_t* feat_on, int64_t F,
+                      int64_t n_items, int64_t num_points, int dedupe_pixels, int64_t* view_ptr,
+                      int64_t* images_out, int64_t* atomic_ptr, void* pixels_out, float* feat_out,
+                      int64_t* order_out, int64_t* counts, void* workspace, size_t workspace_bytes, void* stream);
+int dva_view_cat_sorting(const int64_t* const* ptrs, const int64_t* bases, int64_t S, int64_t N,
+                         int64_t* sorting, int64_t* csr_cat, void* stream);
 
 /* C1  CSR pointers from sorted dense ids     replaces csr.py:158-172 + :197-229
  *   ids [n] int64 sorted ascending, values in [0,num_groups) -> ptr [num_groups+1] int64 with

@@ -55,7 +55,7 @@ def test_knobs_and_workspace_queries_validate_arguments():
     assert lib.dva_linear_gemm_workspace_bytes(100000, 32, 33, 0, 0) >= 16
     small = lib.dva_linear_gemm_workspace_bytes(100000, 32, 33, 2, 0)
     assert small >= 32 * 33 * 4
-    # wide layers need 16-byte rows for TMA: K % 4 != 0 has no workspace (host falls back to a library GEMM)
+    # wide layers need 16-byte rows for TMA: K % 4 != 0 has no workspace (ops.linear zero-pads such widths)
     assert lib.dva_linear_gemm_workspace_bytes(1000, 128, 132, 0, 0) > 0
     assert lib.dva_linear_gemm_workspace_bytes(1000, 128, 131, 0, 0) == 0
     rc = lib.dva_linear_gemm(None, None, None, 10, 128, 131, 0, 0, None, 0, None)

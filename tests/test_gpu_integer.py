@@ -197,3 +197,71 @@ def test_map_images_equals_per_image_oracle():
     assert np.array_equal(_np(m.pointers), ref["pointers"]) and np.array_equal(_np(m.images), ref["images"])
     assert np.array_equal(_np(m.atomic_csr_indexing), ref["atomic_pointers"])
     assert np.array_equal(_np(m.pixels).astype(np.int64), ref["pixels"])
+
+
+def _mapping_equal(a, b):
+    """two ImageMappings (any device): integers bit-exact, pixels in the same order, features to 1e-6"""
+    assert torch.equal(a.pointers.cpu(), b.pointers.cpu())
+    assert torch.equal(a.images.cpu(), b.images.cpu())
+    assert torch.equal(a.values[1].pointers.cpu(), b.values[1].pointers.cpu())
+    assert a.pixels.dtype == b.pixels.dtype and torch.equal(a.pixels.cpu(), b.pixels.cpu())
+    if a.has_features or b.has_features:
+        assert torch.allclose(a.features.cpu(), b.features.cpu(), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("n_points,n_items,n_img,pix_dtype", [(5000, 60000, 7, torch.int16), (300, 40000, 3, torch.int32),
+                                                            (100000, 300000, 40, torch.int16), (10, 0, 1, torch.int16),
+                                                            (1, 1, 1, torch.int64)])
+def test_native_mapping_build_equals_host_path(n_points, n_items, n_img, pix_dtype):
+    """dva_mapping_build (bucket by point + warp rank sort; csrc/mapping_build.cu) == the torch-sort host path
+    (itself pinned on the executed reference, tests/test_containers.py) for from_dense and for
+    select_points('merge'): unseen points, multi-pixel views, buckets longer than a warp (300 points x
+    40 000 items -> ~130 items per point), duplicated (point, image, pixel) triples."""
+    from deepviewagg_b200.core.multimodal.image import ImageMapping
+    gen = torch.Generator().manual_seed(n_items + n_points)
+    pid = torch.randint(0, max(n_points - 3, 1), (n_items,), generator=gen)            # the last points stay unseen
+    iid = torch.randint(0, n_img, (n_items,), generator=gen)
+    pix = torch.randint(0, 50, (n_items, 2), generator=gen).to(pix_dtype)
+    feat = torch.rand(n_items, 8, generator=gen)
+    ref = ImageMapping.from_dense(pid, iid, pix, feat, num_points=n_points)             # CPU tensors: torch sorts
+    got = ImageMapping.from_dense(pid.cuda(), iid.cuda(), pix.cuda(), feat.cuda(), num_points=n_points)
+    _mapping_equal(got, ref)
+    nof = ImageMapping.from_dense(pid.cuda(), iid.cuda(), pix.cuda(), None, num_points=n_points)
+    assert not nof.has_features and torch.equal(nof.images.cpu(), ref.images)
+    if n_items == 0:
+        return
+    # merge: agglomerate points 4 -> 1 (every output voxel present), duplicates removed, features averaged per view
+    n_out = max(n_points // 4, 1)
+    idx = torch.randint(0, n_out, (n_points,), generator=gen)
+    idx[:n_out] = torch.arange(n_out)
+    ref_m = ref.select_points(idx, mode="merge")
+    got_m = got.select_points(idx.cuda(), mode="merge")
+    assert torch.equal(got_m.pointers.cpu(), ref_m.pointers) and torch.equal(got_m.images.cpu(), ref_m.images)
+    ap = ref_m.values[1].pointers
+    assert torch.equal(got_m.values[1].pointers.cpu(), ap)
+    from test_containers import canon_pixels
+    assert torch.equal(canon_pixels(got_m.pixels.cpu(), ap), canon_pixels(ref_m.pixels, ap))
+    assert torch.allclose(got_m.features.cpu(), ref_m.features, rtol=1e-5, atol=1e-6)
+    with pytest.raises(IndexError):
+        ImageMapping.from_dense(pid.cuda() + n_points, iid.cuda(), pix.cuda(), None, num_points=n_points)
+
+
+def test_view_cat_sorting_closed_form_equals_stable_argsort():
+    from deepviewagg_b200.core.multimodal.image import ImageData, ImageMapping, SameSettingImageData
+    gen = torch.Generator().manual_seed(12)
+    N = 20000
+    ims = []
+    for s, (n_img, n_items) in enumerate(((4, 90000), (2, 30000), (3, 0), (5, 150000))):
+        pid = torch.randint(0, N, (n_items,), generator=gen)
+        iid = torch.randint(0, n_img, (n_items,), generator=gen)
+        pix = torch.randint(0, 32, (n_items, 2), generator=gen).short()
+        im = SameSettingImageData(pos=torch.zeros(n_img, 3), opk=torch.zeros(n_img, 3), ref_size=(32 + s, 32),
+                                  proj_upscale=1, downscale=1)
+        im.mappings = ImageMapping.from_dense(pid, iid, pix, torch.rand(n_items, 8, generator=gen), num_points=N)
+        ims.append(im)
+    cpu = ImageData(ims)
+    gpu = cpu.to("cuda")
+    assert torch.equal(gpu.view_cat_sorting.cpu(), cpu.view_cat_sorting)            # stable order of equal points
+    assert torch.equal(gpu.view_cat_csr_indexing.cpu(), cpu.view_cat_csr_indexing)
+    srt, csr = gpu._view_cat_native()
+    assert torch.equal(csr.cpu(), cpu.view_cat_csr_indexing)

@@ -506,7 +506,11 @@ def test_tc_linear_vs_fp64(M, K, N):
     ref = x.double() @ w.double().t()
     ref_gx = g.double() @ w.double()
     ref_gw = g.double().t() @ x.double()
-    for mode, tol in (("fp32", 2e-6), ("tf32", 2e-3)):
+    # 3xTF32 on the tensor cores: ~1e-6 of the result's max at K <= 128, growing with the length of the
+    # fp32 accumulation (K for y / grad_x, the M rows for grad_w); cuBLAS' own fp32 SIMT GEMM is 4e-7 .. 2e-6
+    tol_k = 2e-6 if K <= 128 else 6e-6
+    tol_m = 2e-6 * max(1.0, math.sqrt(M / 4096.0))
+    for mode, tol in (("fp32", tol_k), ("tf32", 2e-3)):
         ops.set_gemm_precision(mode)
         try:
             y = ops.linear(x, w)
@@ -515,8 +519,8 @@ def test_tc_linear_vs_fp64(M, K, N):
             ops.set_gemm_precision("fp32")
         close(y, ref, tol, f"linear {mode}")
         close(gx, ref_gx, tol, f"linear grad_x {mode}")
-        close(gw, ref_gw, tol, f"linear grad_w {mode}")
-    # wide shapes the TMA kernel cannot take fall back to the library GEMM, same values
+        close(gw, ref_gw, max(tol, tol_m), f"linear grad_w {mode}")
+    # widths that are not a multiple of 4 are zero-padded onto the same kernels (no library GEMM)
     x2 = torch.randn(100, 130, generator=gen).cuda()
     w2 = torch.randn(66, 130, generator=gen).cuda()
-    close(ops.linear(x2, w2), x2 @ w2.t(), 1e-6, "fallback")
+    close(ops.linear(x2, w2).double(), x2.double() @ w2.double().t(), 3e-6, "padded widths")

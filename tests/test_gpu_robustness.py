@@ -97,9 +97,9 @@ def test_linear_odd_widths_run_on_our_kernels(K, N):
     gz = torch.randn_like(z)
     gx, gw = torch.autograd.grad(z, [x, w], gz)
     ref = x.double() @ w.double().t()
-    close(z.double(), ref, 2e-6, "padded linear")
-    close(gx.double(), gz.double() @ w.double(), 2e-6, "padded dX")
-    close(gw.double(), gz.double().t() @ x.double(), 2e-6, "padded dW")
+    close(z.double(), ref, 3e-6, "padded linear")
+    close(gx.double(), gz.double() @ w.double(), 3e-6, "padded dX")
+    close(gw.double(), gz.double().t() @ x.double(), 3e-6, "padded dW")
     with pytest.raises(RuntimeError):
         ops.linear(x.cpu(), w.cpu())
 
