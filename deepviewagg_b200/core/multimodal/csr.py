@@ -94,6 +94,10 @@ class CSRData(object):
 
     @property
     def num_items(self):
+        # the value tensors know their length on the host: no device read (csr.py:113 reads pointers[-1])
+        if self.values:
+            v = self.values[0]
+            return int(v.num_groups) if isinstance(v, CSRData) else int(v.shape[0])
         return int(self.pointers[-1].item())
 
     @staticmethod
@@ -204,11 +208,11 @@ class CSRBatch(CSRData):
             if isinstance(vals[0], CSRData):
                 val = CSRBatch.from_csr_list(vals)
             elif bool(is_index_value[i]):
-                shifts, run = [], 0
-                for v in vals:
-                    shifts.append(run)
-                    run += (int(v.max().item()) + 1) if v.shape[0] > 0 else 0
-                val = torch.cat([v + s for v, s in zip(vals, shifts)], dim=0)
+                # running max + 1 of the previous items (csr.py:391-402), kept on the device: no .item()
+                zero = torch.zeros((), dtype=vals[0].dtype, device=device)
+                tops = torch.stack([(v.max() + 1) if v.shape[0] > 0 else zero for v in vals])
+                shifts = torch.cumsum(tops, 0) - tops
+                val = torch.cat([v + shifts[j] for j, v in enumerate(vals)], dim=0)
             else:
                 val = torch.cat(vals, dim=0)
             values.append(val)

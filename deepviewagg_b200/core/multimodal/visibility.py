@@ -234,7 +234,10 @@ def postprocess_features(xyz_to_img, y_proj, dist, linearity, planarity, scatter
     planarity, scattering, |cos(view, normal)|, normalised pixel height."""
     features = []
     if dist is not None:
-        features.append(((dist.float() - r_min) / (r_max + 1e-4)).float())
+        # tensor / tensor: a CUDA division by a Python scalar is evaluated as a multiplication by its
+        # reciprocal (1 ulp off the reference's CPU result, normalize_dist_cuda visibility.py:1503-1518)
+        d = dist.float()
+        features.append(((d - r_min) / torch.full_like(d, r_max + 1e-4)).float())
     for f in (linearity, planarity, scattering):
         if f is not None:
             features.append(f)
@@ -243,7 +246,7 @@ def postprocess_features(xyz_to_img, y_proj, dist, linearity, planarity, scatter
         p = u * normals.float()
         features.append(((p[:, 0] + p[:, 1]) + p[:, 2]).abs())           # torch CPU's sum order over 3 terms
     if y_proj is not None:
-        features.append((y_proj / img_size[1]).float())
+        features.append((y_proj / torch.full_like(y_proj, float(img_size[1]))).float())
     return torch.stack(features).t()
 
 

@@ -17,6 +17,16 @@ extern "C" int dva_tc_dw_gemm(const float* dZ, const float* X, float* D, int64_t
 
 using namespace dva;
 
+// Which family serves a shape.  The skinny mma.sync kernels take every K, N <= 64; measured on the B200
+// (1.28 M rows): 64 -> 64 forward / dX 0.25 / 0.19 ms on the skinny kernels against 0.146 ms on the tcgen05 rows
+// kernel, 32-wide layers on a par (0.07 - 0.08 ms) -> rows kernels (layouts 0, 1) go to tcgen05 when both widths
+// exceed 32 and are multiples of 4; dW (layout 2) stays on the skinny kernel up to 64 x 64.
+static bool use_skinny(int64_t M, int64_t N, int64_t K, int layout) {
+  if (!dva_skinny_gemm_supported(M, N, K, layout)) return false;
+  if (layout == 2) return true;
+  return !(N > 32 && K > 32 && N % 4 == 0 && K % 4 == 0);
+}
+
 static bool gemm_shape_ok(int64_t M, int64_t N, int64_t K) {
   return M >= 1 && N >= 4 && K >= 4 && N % 4 == 0 && K % 4 == 0 && M < (1ll << 40) && N <= 65536 && K <= 65536;
 }
@@ -25,7 +35,7 @@ extern "C" size_t dva_linear_gemm_workspace_bytes(int64_t M, int64_t N, int64_t 
   (void)precision;
   // narrow projections (both small dimensions <= 64: every MLP of the map encoders) run on the
   // 3xTF32 mma.sync kernels of skinny_gemm.cu
-  if (dva_skinny_gemm_supported(M, N, K, layout)) return dva_skinny_gemm_workspace_bytes(M, N, K, layout);
+  if (use_skinny(M, N, K, layout)) return dva_skinny_gemm_workspace_bytes(M, N, K, layout);
   if (!gemm_shape_ok(M, N, K)) return 0;
   size_t w;
   if (layout == 0 || layout == 1) w = dva_tc_rows_workspace_bytes(N, K);   // split weight [n_out = N, reduction = K]
@@ -38,7 +48,7 @@ extern "C" int dva_linear_gemm(const float* A, const float* B, float* D, int64_t
                                void* stream) {
   if (layout < 0 || layout > 2 || (precision != 0 && precision != 1)) return fail(DVA_EINVAL, "linear_gemm: bad layout/precision");
   if (M == 0 && layout != 2) return DVA_OK;
-  if (M > 0 && dva_skinny_gemm_supported(M, N, K, layout))
+  if (M > 0 && use_skinny(M, N, K, layout))
     return dva_skinny_gemm(A, B, D, M, N, K, layout, workspace, workspace_bytes, stream);
   if (M > 0 && !gemm_shape_ok(M, N, K)) return fail(DVA_EUNSUPPORTED, "linear_gemm: N and K must be multiples of 4 (16-byte TMA rows)");
   if (!A || !B || !D) return fail(DVA_EINVAL, "linear_gemm: null pointer");

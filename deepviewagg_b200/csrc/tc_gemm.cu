@@ -38,10 +38,12 @@ namespace tc {
 constexpr int kTile = 128;                 // rows of X per tile (UMMA N) and output columns per tile (UMMA M)
 constexpr int kBK = 32;                    // fp32 per k-block: one 128-byte swizzle row
 constexpr int kTileBytes = kTile * kBK * 4;  // 16 KB
-constexpr int kStages = 3;
+constexpr int kStages = 3;                 // stages of the streamed-weight rows kernel and of the dw kernel
+constexpr int kStagesT = 6;                // stages of the rows kernel with the weight in tensor memory
 constexpr int kThreads = 320;
 constexpr int kSplitThreads = 128;
-constexpr uint32_t kTmemCols = 256;
+constexpr uint32_t kTmemCols = 256;        // two 128-column accumulators
+constexpr uint32_t kTmemColsW = 512;       // + weight hi at column 256, weight lo at column 384 (K <= 128 each)
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -89,6 +91,27 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same with the A operand (the weight tile: 128 lanes x K tf32 columns) read from tensor memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// 32 registers per thread -> 32 TMEM lanes (this warp's quadrant) x 32 consecutive columns
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // mbarrier arrive once every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -140,6 +163,8 @@ split_weight_kernel(const float* __restrict__ W, float* __restrict__ hi, float* 
 
 // ---- rows kernel --------------------------------------------------------------------------------------------
 struct RowsParams {
+  const float *w_hi, *w_lo;   // split weight [n_pad, k_red] row-major (read directly by the WTMEM variant)
+  int k_red;
   float* out;            // [M, n_out] row-major, leading dimension ldo
   float* col_stats;      // nullptr or [gridDim.x, 3, 128] per-CTA (sum (v - shift), sum (v - shift)^2, shift) per column
   int64_t M;
@@ -147,7 +172,12 @@ struct RowsParams {
   int64_t m_tiles;
 };
 
-template <bool RESIDENT>
+// WTMEM = true : K <= 128 and one column tile: the weight (hi, lo) lives in TENSOR MEMORY for the whole kernel
+//                (tcgen05.mma with the A operand from TMEM): shared memory only carries the X stages (6 x 32 KB)
+//                and the tensor core's operand reads from shared memory are halved -- the N = 128 MMA at full
+//                rate would otherwise eat the whole 128 B/clk of shared-memory bandwidth by itself;
+// WTMEM = false: wider layers: weight k-blocks are streamed through shared memory next to X (3 x 64 KB).
+template <bool WTMEM>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_rows_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
                const __grid_constant__ CUtensorMap map_wlo, const RowsParams p) {
@@ -155,33 +185,33 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   // 1024-byte alignment: swizzle atoms are addressed relative to 1024-byte boundaries
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int KB = p.k_blocks;
-  // layout: [resident W: hi k-blocks | lo k-blocks] [stages: X_hi, X_lo (, W_hi, W_lo)] [barriers]
-  const uint32_t w_bytes = RESIDENT ? 2u * KB * kTileBytes : 0u;
-  constexpr uint32_t kStageBytes = (RESIDENT ? 2u : 4u) * kTileBytes;
-  uint8_t* w_base = smem;
-  uint8_t* st_base = smem + w_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(st_base + kStages * kStageBytes);
-  // barriers: full_tma[3] full_cvt[3] empty[3] tmem_full[2] tmem_empty[2] w_full[1]; then the TMEM base word
+  constexpr int NS = WTMEM ? kStagesT : kStages;
+  // stage: X_hi, X_lo (, W_hi, W_lo); then the barriers
+  constexpr uint32_t kStageBytes = (WTMEM ? 2u : 4u) * kTileBytes;
+  uint8_t* st_base = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(st_base + NS * kStageBytes);
+  // barriers: full_tma[NS] full_cvt[NS] empty[NS] tmem_full[2] tmem_empty[2] w_full[1]; then the TMEM base word
   const uint32_t bar0 = smem_u32(bars);
   auto full_tma = [&](int s) { return bar0 + 8u * s; };
-  auto full_cvt = [&](int s) { return bar0 + 8u * (kStages + s); };
-  auto empty = [&](int s) { return bar0 + 8u * (2 * kStages + s); };
-  auto tmem_full = [&](int a) { return bar0 + 8u * (3 * kStages + a); };
-  auto tmem_empty = [&](int a) { return bar0 + 8u * (3 * kStages + 2 + a); };
-  const uint32_t w_full = bar0 + 8u * (3 * kStages + 4);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 5);
+  auto full_cvt = [&](int s) { return bar0 + 8u * (NS + s); };
+  auto empty = [&](int s) { return bar0 + 8u * (2 * NS + s); };
+  auto tmem_full = [&](int a) { return bar0 + 8u * (3 * NS + a); };
+  auto tmem_empty = [&](int a) { return bar0 + 8u * (3 * NS + 2 + a); };
+  const uint32_t w_full = bar0 + 8u * (3 * NS + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * NS + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t tiles = p.m_tiles * p.n_tiles;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_whi); tma_prefetch_desc(&map_wlo);
-    for (int s = 0; s < kStages; ++s) { mbar_init(full_tma(s), 1); mbar_init(full_cvt(s), kSplitThreads / 32); mbar_init(empty(s), 1); }
+    tma_prefetch_desc(&map_x);
+    if (!WTMEM) { tma_prefetch_desc(&map_whi); tma_prefetch_desc(&map_wlo); }
+    for (int s = 0; s < NS; ++s) { mbar_init(full_tma(s), 1); mbar_init(full_cvt(s), kSplitThreads / 32); mbar_init(empty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 4); }
-    mbar_init(w_full, 1);
+    mbar_init(w_full, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), WTMEM ? kTmemColsW : kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -190,13 +220,6 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      if (RESIDENT) {
-        mbar_expect_tx(w_full, w_bytes);
-        for (int kb = 0; kb < KB; ++kb) {
-          tma_load_2d(smem_u32(w_base + (size_t)kb * kTileBytes), &map_whi, kb * kBK, 0, w_full);
-          tma_load_2d(smem_u32(w_base + (size_t)(KB + kb) * kTileBytes), &map_wlo, kb * kBK, 0, w_full);
-        }
-      }
       int s = 0; uint32_t ph = 0;
       for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
         const int64_t mt = t / p.n_tiles;
@@ -204,20 +227,20 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(empty(s), ph ^ 1u);
           uint8_t* st = st_base + (size_t)s * kStageBytes;
-          mbar_expect_tx(full_tma(s), RESIDENT ? kTileBytes : 3u * kTileBytes);
+          mbar_expect_tx(full_tma(s), WTMEM ? kTileBytes : 3u * kTileBytes);
           tma_load_2d(smem_u32(st), &map_x, kb * kBK, (int)(mt * kTile), full_tma(s));
-          if (!RESIDENT) {
+          if (!WTMEM) {
             tma_load_2d(smem_u32(st + 2 * kTileBytes), &map_whi, kb * kBK, nt * kTile, full_tma(s));
             tma_load_2d(smem_u32(st + 3 * kTileBytes), &map_wlo, kb * kBK, nt * kTile, full_tma(s));
           }
-          if (++s == kStages) { s = 0; ph ^= 1u; }
+          if (++s == NS) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      if (RESIDENT) mbar_wait(w_full, 0);
+      if (WTMEM) { mbar_wait(w_full, 0); tc_fence_after(); }
       int s = 0; uint32_t ph = 0; int acc = 0; uint32_t aph = 0;
       for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
         mbar_wait(tmem_empty(acc), aph ^ 1u);
@@ -230,18 +253,29 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           uint8_t* st = st_base + (size_t)s * kStageBytes;
           const uint64_t x_hi = smem_desc_k_sw128(smem_u32(st));
           const uint64_t x_lo = smem_desc_k_sw128(smem_u32(st + kTileBytes));
-          const uint64_t w_hi = smem_desc_k_sw128(smem_u32(RESIDENT ? w_base + (size_t)kb * kTileBytes : st + 2 * kTileBytes));
-          const uint64_t w_lo = smem_desc_k_sw128(smem_u32(RESIDENT ? w_base + (size_t)(KB + kb) * kTileBytes : st + 3 * kTileBytes));
+          if (WTMEM) {
+            const uint32_t w_hi = tmem_base + 256u + (uint32_t)kb * kBK, w_lo = tmem_base + 384u + (uint32_t)kb * kBK;
 #pragma unroll
-          for (int k = 0; k < kBK / 8; ++k) {           // UMMA_K = 8 tf32 = 32 bytes: +2 in the 16-byte address field
-            const uint64_t o = (uint64_t)(2 * k);
-            umma_tf32(d, w_lo + o, x_hi + o, kIdescTf32, (uint32_t)((kb | k) != 0));
-            umma_tf32(d, w_hi + o, x_lo + o, kIdescTf32, 1u);
-            umma_tf32(d, w_hi + o, x_hi + o, kIdescTf32, 1u);
+            for (int k = 0; k < kBK / 8; ++k) {         // UMMA_K = 8 tf32: 8 TMEM columns of W, 32 bytes of X
+              const uint64_t o = (uint64_t)(2 * k);
+              umma_tf32_ts(d, w_lo + 8u * k, x_hi + o, kIdescTf32, (uint32_t)((kb | k) != 0));
+              umma_tf32_ts(d, w_hi + 8u * k, x_lo + o, kIdescTf32, 1u);
+              umma_tf32_ts(d, w_hi + 8u * k, x_hi + o, kIdescTf32, 1u);
+            }
+          } else {
+            const uint64_t w_hi = smem_desc_k_sw128(smem_u32(st + 2 * kTileBytes));
+            const uint64_t w_lo = smem_desc_k_sw128(smem_u32(st + 3 * kTileBytes));
+#pragma unroll
+            for (int k = 0; k < kBK / 8; ++k) {         // UMMA_K = 8 tf32 = 32 bytes: +2 in the 16-byte address field
+              const uint64_t o = (uint64_t)(2 * k);
+              umma_tf32(d, w_lo + o, x_hi + o, kIdescTf32, (uint32_t)((kb | k) != 0));
+              umma_tf32(d, w_hi + o, x_lo + o, kIdescTf32, 1u);
+              umma_tf32(d, w_hi + o, x_hi + o, kIdescTf32, 1u);
+            }
           }
           umma_commit(empty(s));                         // stage reusable once these MMAs have read it
           if (kb == KB - 1) umma_commit(tmem_full(acc)); // accumulator complete
-          if (++s == kStages) { s = 0; ph ^= 1u; }
+          if (++s == NS) { s = 0; ph ^= 1u; }
         }
         if (++acc == 2) { acc = 0; aph ^= 1u; }
       }
@@ -268,13 +302,34 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         fence_proxy_async();                             // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(full_cvt(s));
-        if (++s == kStages) { s = 0; ph ^= 1u; }
+        if (++s == NS) { s = 0; ph ^= 1u; }
       }
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> coalesced global stores =====================
     const int q = warp & 3;                              // TMEM lane quadrant this warp may access
     const int col = q * 32 + lane;                       // output column within the tile (TMEM lane)
+    if (WTMEM) {
+      // the weight tile into tensor memory: lane = output column, TMEM column = k (row-major prep buffers
+      // [128, K], zero padded rows); 32 columns per tcgen05.st
+      const float* whi = p.w_hi + (int64_t)col * p.k_red;
+      const float* wlo = p.w_lo + (int64_t)col * p.k_red;
+      for (int c0 = 0; c0 < KB * kBK; c0 += 32) {
+        uint32_t rh[32], rl[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const bool ok = c0 + j < p.k_red;
+          rh[j] = ok ? __float_as_uint(whi[c0 + j]) : 0u;
+          rl[j] = ok ? __float_as_uint(wlo[c0 + j]) : 0u;
+        }
+        tmem_st_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)c0, rh);
+        tmem_st_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + 384u + (uint32_t)c0, rl);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(w_full);
+    }
     // BatchNorm column statistics (single n tile only): sums of (v - shift) and (v - shift)^2, shifted by
     // the first value this thread sees (no catastrophic cancellation in the variance); every CTA has its
     // own shift, bn_stats_finalize_kernel recombines them in fp64
@@ -334,7 +389,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc(tmem_base, WTMEM ? kTmemColsW : kTmemCols);
   }
 }
 
@@ -624,6 +679,7 @@ extern "C" int dva_tc_rows_gemm(const float* X, const float* W, float* D, int64_
   rc = tc::make_map(&ml, wlo, n_pad, k_red, k_red, tc::kTile);
   if (rc) return rc;
   tc::RowsParams p;
+  p.w_hi = whi; p.w_lo = wlo; p.k_red = (int)k_red;
   p.out = D; p.col_stats = col_stats; p.M = M; p.n_out = (int)n_out; p.n_tiles = n_pad / tc::kTile;
   p.k_blocks = (int)((k_red + tc::kBK - 1) / tc::kBK); p.ldo = (int)ldo; p.m_tiles = (M + tc::kTile - 1) / tc::kTile;
   const bool resident = p.n_tiles == 1 && p.k_blocks <= 4;
@@ -631,8 +687,7 @@ extern "C" int dva_tc_rows_gemm(const float* X, const float* W, float* D, int64_
   const int64_t tiles = p.m_tiles * p.n_tiles;
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
   if (stats_ctas) *stats_ctas = grid;
-  const size_t smem = 1024 + (resident ? (size_t)2 * p.k_blocks * tc::kTileBytes : 0) +
-                      (size_t)tc::kStages * (resident ? 2 : 4) * tc::kTileBytes + 256;
+  const size_t smem = 1024 + (resident ? (size_t)tc::kStagesT * 2 : (size_t)tc::kStages * 4) * tc::kTileBytes + 256;
   cudaError_t e;
   if (resident) {
     e = cudaFuncSetAttribute(tc::tc_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -713,7 +768,7 @@ extern "C" size_t dva_linear_bnstats_workspace_bytes(int64_t n_out, int64_t k_re
 }
 
 extern "C" int dva_linear_bnstats_supported(int64_t M, int64_t n_out, int64_t k_red) {
-  return dva_tc_rows_supported(M, n_out, k_red) && n_out <= tc::kTile && n_out % 4 == 0 && !(n_out <= 64 && k_red <= 64);
+  return dva_tc_rows_supported(M, n_out, k_red) && n_out <= tc::kTile && n_out % 4 == 0 && n_out > 32 && k_red > 32;
 }
 
 extern "C" int dva_linear_bnstats_fwd(const float* X, const float* W, float* D, int64_t M, int64_t n_out,

@@ -52,8 +52,8 @@ project_equirect_kernel(const float* __restrict__ xyz, const float* __restrict__
     const float p = dva_acosf(__fdiv_rn(v2, d));
     double w = ((double)(W - 1) * (1.0 - (double)t / PI) / 2.0);
     double h = ((double)(H - 1) * (double)p / PI);
-    w = w - floor(w / (double)W) * (double)W;      // numpy/python '%': result has divisor's sign
-    h = h - floor(h / (double)H) * (double)H;
+    w = __dsub_rn(w, __dmul_rn(floor(w / (double)W), (double)W));   // numpy/python '%' (no DFMA contraction)
+    h = __dsub_rn(h, __dmul_rn(floor(h / (double)H), (double)H));
     if (w != w) w = 0.0;
     if (h != h) h = 0.0;
     x_proj[i] = w; y_proj[i] = h;
@@ -97,15 +97,19 @@ project_camera_kernel(const float* __restrict__ xyz, const float* __restrict__ c
       z = (double)p2;
     } else {
       const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(p0, p0), __fmul_rn(p1, p1)), __fmul_rn(p2, p2)));
-      const double den = (double)nrm + 1e-4;
-      double fx = (double)p0 / den, fy = (double)p1 / den;
-      const double fz = (double)p2 / den;
-      fx /= fz + (double)in[0];
-      fy /= fz + (double)in[0];
-      const double r2 = fx * fx + fy * fy, r4 = r2 * r2;
-      x = (double)in[3] * (1.0 + (double)in[1] * r2 + (double)in[2] * r4) * fx + (double)in[5];
-      y = (double)in[4] * (1.0 + (double)in[1] * r2 + (double)in[2] * r4) * fy + (double)in[6];
-      z = (double)__fmul_rn(nrm, p2) / fabs((double)p2 + 1e-4);
+      // float64 like numba (visibility.py:323-336); every product / sum rounded on its own -- nvcc would
+      // otherwise contract a * b + c into one DFMA, which LLVM (numba) and gcc -ffp-contract=off do not
+      const double den = __dadd_rn((double)nrm, 1e-4);
+      double fx = __ddiv_rn((double)p0, den), fy = __ddiv_rn((double)p1, den);
+      const double fz = __ddiv_rn((double)p2, den);
+      const double dz_ = __dadd_rn(fz, (double)in[0]);
+      fx = __ddiv_rn(fx, dz_);
+      fy = __ddiv_rn(fy, dz_);
+      const double r2 = __dadd_rn(__dmul_rn(fx, fx), __dmul_rn(fy, fy)), r4 = __dmul_rn(r2, r2);
+      const double poly = __dadd_rn(__dadd_rn(1.0, __dmul_rn((double)in[1], r2)), __dmul_rn((double)in[2], r4));
+      x = __dadd_rn(__dmul_rn(__dmul_rn((double)in[3], poly), fx), (double)in[5]);
+      y = __dadd_rn(__dmul_rn(__dmul_rn((double)in[4], poly), fy), (double)in[6]);
+      z = __ddiv_rn((double)__fmul_rn(nrm, p2), fabs(__dadd_rn((double)p2, 1e-4)));
     }
     x_proj[i] = x; y_proj[i] = y;
     const bool in_range = (r_min < d) && (d < r_max);
@@ -129,7 +133,7 @@ splat_boxes_kernel(const double* __restrict__ x_proj, const double* __restrict__
     const double d = (double)dist[i];
     const double xp = x_proj[i], yp = y_proj[i];
     // (1 + k_swell * exp(-dist / log(d_swell))) * voxel / dist   (visibility.py:651-652, :783)
-    const double swell = (1.0 + k_swell * exp(-d / log_d_swell)) * voxel / d;
+    const double swell = __dadd_rn(1.0, __dmul_rn(k_swell, exp(-d / log_d_swell))) * voxel / d;   // no DFMA contraction
     double wx, wy;
     if (camera == 0) {
       wy = swell * (double)H / PI;

@@ -240,8 +240,8 @@ int dva_linear_gemm(const float* A, const float* B, float* D, int64_t M, int64_t
  *   shifted sum / sum of squares while storing; a one-warp-per-column kernel combines the per-CTA
  *   partials in fp64 (fixed order) into mean / invstd [n_out] (biased variance) and updates the running
  *   buffers (momentum, unbiased variance) like nn.BatchNorm1d.  The apply half is dva_bn_act_fwd with
- *   training = 0 on these mean / invstd.  supported(): n_out <= 128, n_out % 4 == 0, k_red % 4 == 0 and
- *   not a skinny shape (n_out <= 64 and k_red <= 64); else DVA_EUNSUPPORTED.
+ *   training = 0 on these mean / invstd.  supported(): 32 < n_out <= 128, n_out % 4 == 0, k_red > 32,
+ *   k_red % 4 == 0 (the shapes dva_linear_gemm serves with the tcgen05 rows kernel); else DVA_EUNSUPPORTED.
  * ------------------------------------------------------------------------------------------ */
 int dva_linear_bnstats_supported(int64_t M, int64_t n_out, int64_t k_red);
 size_t dva_linear_bnstats_workspace_bytes(int64_t n_out, int64_t k_red);
