@@ -407,13 +407,15 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 constexpr int kDwRows = 32;                      // contraction rows per stage
 constexpr int kGroupBytes = kDwRows * 128;       // one [32 x 32] box
 constexpr int kDwOperandBytes = 4 * kGroupBytes; // 4 column groups = 128 columns: 16 KB
-constexpr uint32_t kDwTmemCols = 128;
+constexpr int kDwStages = 4;
+constexpr uint32_t kDwTmemCols = 512;            // accumulator [0,128) + per stage dZ_hi | dZ_lo (32 + 32 columns)
 
 __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr) {
   return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)(kGroupBytes >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
          (1ull << 46) | (1ull << 61);
 }
-constexpr uint32_t kIdescTf32MN = kIdescTf32 | (1u << 15) | (1u << 16);   // A and B MN-major
+// A (dZ^T) from tensor memory: K-major by construction; B (X) MN-major in shared memory
+constexpr uint32_t kIdescTf32TsMN = kIdescTf32 | (1u << 16);
 
 struct DwParams {
   float* partial;        // [splits, n_pad, k_pad]
@@ -421,18 +423,25 @@ struct DwParams {
   int n_out, k_in, n_pad, k_pad, k_tiles, splits;
 };
 
+// The dZ operand never goes back to shared memory: split warp g (TMEM lane quadrant g = output rows 32 g ..)
+// reads column n = 32 g + lane of the landed [32 x 128] tile row by row (a warp-wide LDS of one 128-byte row:
+// conflict-free whatever the swizzle), splits it and stores hi / lo TRANSPOSED into tensor memory with one
+// tcgen05.st each -- lane = output row, 32 columns = the 32 contraction rows of the stage.  The tensor core
+// then reads A from TMEM and only X from shared memory: 144 KB instead of 224 KB of shared-memory traffic
+// per 32 KB of HBM traffic (the all-shared-memory version was bound by the 128 B/clk of shared memory).
 __global__ void __launch_bounds__(kThreads, 1)
 tc_dw_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__ CUtensorMap map_x, const DwParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr uint32_t kStageBytes = 4u * kDwOperandBytes;      // dZ_hi, dZ_lo, X_hi, X_lo
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  constexpr int NS = kDwStages;
+  constexpr uint32_t kStageBytes = 3u * kDwOperandBytes;      // dZ (raw), X_hi, X_lo
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * kStageBytes);
   const uint32_t bar0 = smem_u32(bars);
   auto full_tma = [&](int s) { return bar0 + 8u * s; };
-  auto full_cvt = [&](int s) { return bar0 + 8u * (kStages + s); };
-  auto empty = [&](int s) { return bar0 + 8u * (2 * kStages + s); };
-  const uint32_t tmem_full = bar0 + 8u * (3 * kStages);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
+  auto full_cvt = [&](int s) { return bar0 + 8u * (NS + s); };
+  auto empty = [&](int s) { return bar0 + 8u * (2 * NS + s); };
+  const uint32_t tmem_full = bar0 + 8u * (3 * NS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * NS + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int split = blockIdx.x % p.splits, tile = blockIdx.x / p.splits;
@@ -446,7 +455,7 @@ tc_dw_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_dz); tma_prefetch_desc(&map_x);
-    for (int s = 0; s < kStages; ++s) { mbar_init(full_tma(s), 1); mbar_init(full_cvt(s), kSplitThreads / 32); mbar_init(empty(s), 1); }
+    for (int s = 0; s < NS; ++s) { mbar_init(full_tma(s), 1); mbar_init(full_cvt(s), kSplitThreads / 32); mbar_init(empty(s), 1); }
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -467,8 +476,8 @@ tc_dw_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__
         for (int g = 0; g < a_groups; ++g)
           tma_load_2d(smem_u32(st + g * kGroupBytes), &map_dz, nt * kTile + g * 32, row, full_tma(s));
         for (int g = 0; g < b_groups; ++g)
-          tma_load_2d(smem_u32(st + 2 * kDwOperandBytes + g * kGroupBytes), &map_x, kt * kTile + g * 32, row, full_tma(s));
-        if (++s == kStages) { s = 0; ph ^= 1u; }
+          tma_load_2d(smem_u32(st + kDwOperandBytes + g * kGroupBytes), &map_x, kt * kTile + g * 32, row, full_tma(s));
+        if (++s == NS) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -479,34 +488,49 @@ tc_dw_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__
         mbar_wait(full_cvt(s), ph);
         tc_fence_after();
         uint8_t* st = smem + (size_t)s * kStageBytes;
-        const uint64_t a_hi = smem_desc_mn_sw128(smem_u32(st));
-        const uint64_t a_lo = smem_desc_mn_sw128(smem_u32(st + kDwOperandBytes));
-        const uint64_t x_hi = smem_desc_mn_sw128(smem_u32(st + 2 * kDwOperandBytes));
-        const uint64_t x_lo = smem_desc_mn_sw128(smem_u32(st + 3 * kDwOperandBytes));
+        const uint32_t a_hi = tmem_base + 128u + (uint32_t)s * 64u, a_lo = a_hi + 32u;
+        const uint64_t x_hi = smem_desc_mn_sw128(smem_u32(st + kDwOperandBytes));
+        const uint64_t x_lo = smem_desc_mn_sw128(smem_u32(st + 2 * kDwOperandBytes));
 #pragma unroll
-        for (int k = 0; k < kDwRows / 8; ++k) {          // 8 contraction rows = two 512-byte atoms per group
+        for (int k = 0; k < kDwRows / 8; ++k) {          // 8 contraction rows: 8 TMEM columns of dZ^T, two 512-byte atoms of X
           const uint64_t o = (uint64_t)(k * (1024 >> 4));
-          umma_tf32(tmem_base, a_lo + o, x_hi + o, kIdescTf32MN, (uint32_t)((b | k) != 0));
-          umma_tf32(tmem_base, a_hi + o, x_lo + o, kIdescTf32MN, 1u);
-          umma_tf32(tmem_base, a_hi + o, x_hi + o, kIdescTf32MN, 1u);
+          umma_tf32_ts(tmem_base, a_lo + 8u * k, x_hi + o, kIdescTf32TsMN, (uint32_t)((b | k) != 0));
+          umma_tf32_ts(tmem_base, a_hi + 8u * k, x_lo + o, kIdescTf32TsMN, 1u);
+          umma_tf32_ts(tmem_base, a_hi + 8u * k, x_hi + o, kIdescTf32TsMN, 1u);
         }
         umma_commit(empty(s));
         if (b == nblk - 1) umma_commit(tmem_full);
-        if (++s == kStages) { s = 0; ph ^= 1u; }
+        if (++s == NS) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp < 2 + kSplitThreads / 32) {
     const int tid = threadIdx.x - 64;
+    const int g = warp & 3;                              // TMEM lane quadrant = dZ column group of this warp
     int s = 0; uint32_t ph = 0;
     for (int64_t b = 0; b < nblk; ++b) {
       mbar_wait(full_tma(s), ph);
       uint8_t* st = smem + (size_t)s * kStageBytes;
+      if (g < a_groups) {
+        // dZ column n = 32 g + lane over the 32 rows of the stage -> TMEM (hi, lo); 128B / 32-byte-atom swizzle:
+        // the 32-byte chunk index is XOR-ed with (row & 3)
+        const uint8_t* grp = st + g * kGroupBytes + (lane & 7) * 4;
+        uint32_t rh[32], rl[32];
 #pragma unroll
-      for (int op = 0; op < 2; ++op) {
-        float4* hi = reinterpret_cast<float4*>(st + op * 2 * kDwOperandBytes);
-        float4* lo = reinterpret_cast<float4*>(st + op * 2 * kDwOperandBytes + kDwOperandBytes);
-        const int groups = op == 0 ? a_groups : b_groups;
-        for (int i = 0; i < groups * (kGroupBytes / 16) / kSplitThreads; ++i) {
+        for (int v = 0; v < 32; ++v) {
+          const float x = *reinterpret_cast<const float*>(grp + v * 128 + ((((lane >> 3) ^ (v & 3)) & 3) << 5));
+          const float h = tf32_rna(x);
+          rh[v] = __float_as_uint(h);
+          rl[v] = __float_as_uint(tf32_rna(x - h));
+        }
+        const uint32_t ta = tmem_base + ((uint32_t)(g * 32) << 16) + 128u + (uint32_t)s * 64u;
+        tmem_st_32x32(ta, rh);
+        tmem_st_32x32(ta + 32u, rl);
+        tmem_st_wait();
+      }
+      {
+        float4* hi = reinterpret_cast<float4*>(st + kDwOperandBytes);
+        float4* lo = reinterpret_cast<float4*>(st + 2 * kDwOperandBytes);
+        for (int i = 0; i < b_groups * (kGroupBytes / 16) / kSplitThreads; ++i) {
           const int e = i * kSplitThreads + tid;
           const float4 v = hi[e];
           float4 h, l;
@@ -517,9 +541,10 @@ tc_dw_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__
         }
       }
       fence_proxy_async();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(full_cvt(s));
-      if (++s == kStages) { s = 0; ph ^= 1u; }
+      if (++s == NS) { s = 0; ph ^= 1u; }
     }
   } else {
     // epilogue: lane = output row (n_out index), 32 consecutive k_in columns per tcgen05.ld
@@ -748,7 +773,7 @@ extern "C" int dva_tc_dw_gemm(const float* dZ, const float* X, float* D, int64_t
   if (rc) return rc;
   rc = tc::make_map(&mx, X, V, k_in, ldx, tc::kDwRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (rc) return rc;
-  const size_t smem = 1024 + (size_t)tc::kStages * 4 * tc::kDwOperandBytes + 256;
+  const size_t smem = 1024 + (size_t)tc::kDwStages * 3 * tc::kDwOperandBytes + 256;
   cudaError_t e = cudaFuncSetAttribute(tc::tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail((int)e, "tc_dw_gemm: cannot reserve shared memory");
   tc::tc_dw_kernel<<<nt * kt * sp, tc::kThreads, smem, st>>>(mz, mx, p);

@@ -691,6 +691,7 @@ static std::atomic<int>& va_path() {
     if (e == nullptr) return 0;
     if (strcmp(e, "stream") == 0) return 1;
     if (strcmp(e, "ring") == 0) return 2;
+    if (strcmp(e, "lane") == 0) return 3;
     return 0;
   }()};
   return p;
@@ -706,11 +707,20 @@ static std::atomic<int>& va_path() {
 static bool use_ring(const VAParams& P, int dtype, bool applicable, bool backward) {
   if (!applicable) return false;
   const int path = va_path().load(std::memory_order_relaxed);
-  if (path == 1) return false;
+  if (path == 1 || path == 3) return false;
   if (path == 2) return true;
   if (P.V > (int64_t)DVA_RING_MAX_MEAN_VIEWS * P.N) return false;
   const size_t esz = dtype == DVA_F32 ? 4 : 2;
   return !backward || (size_t)P.C * esz <= 128;
+}
+
+// backward only: the lane-per-view kernel (view_attention_lane.cu) for short segments, path 3 forces it
+static bool use_lane_bwd(const VAParams& P, bool applicable) {
+  if (!applicable) return false;
+  const int path = va_path().load(std::memory_order_relaxed);
+  if (path == 3) return true;
+  if (path != 0) return false;
+  return P.V <= (int64_t)DVA_RING_MAX_MEAN_VIEWS * P.N;
 }
 
 }  // namespace dva
@@ -751,7 +761,7 @@ extern "C" int dva_view_attention_fwd(const void* x, const void* idx, int idx_is
 }
 
 extern "C" int dva_view_attention_set_path(int path) {
-  if (path < 0 || path > 2) return fail(DVA_EINVAL, "view_attention_set_path: 0 = auto, 1 = streaming, 2 = ring");
+  if (path < 0 || path > 3) return fail(DVA_EINVAL, "view_attention_set_path: 0 = auto, 1 = streaming, 2 = ring, 3 = lane (backward)");
   va_path().store(path, std::memory_order_relaxed);
   return DVA_OK;
 }
@@ -795,7 +805,9 @@ extern "C" int dva_view_attention_bwd(const void* x, const void* idx, int idx_is
   int grid = 1;
   int rc;
   if (dtype != DVA_F32 && dtype != DVA_BF16 && dtype != DVA_F16) return fail(DVA_EINVAL, "view_attention_bwd: unknown dtype");
-  if (use_ring(P, dtype, va_ring_bwd_applicable(P, dtype), true)) {
+  if (use_lane_bwd(P, va_lane_bwd_applicable(P, dtype))) {
+    rc = va_lane_bwd(P, dtype, &grid, st);
+  } else if (use_ring(P, dtype, va_ring_bwd_applicable(P, dtype), true)) {
     rc = va_ring_bwd(P, dtype, &grid, st);
   } else {
     switch (dtype) {

@@ -101,11 +101,14 @@ int dva_view_attention_fwd(const void* x, const void* idx, int idx_is_i64, const
                            int64_t G, int group_scaling, float eps, int dtype, void* stream);
 
 /* Implementation choice of the fused pair (tuning / test knob, process-wide; results are the same
- * up to fp32 summation order): 0 = auto (default; also DVA_VA_PATH=auto|stream|ring in the
+ * up to fp32 summation order): 0 = auto (default; also DVA_VA_PATH=auto|stream|ring|lane in the
  * environment), 1 = streaming kernels (rows in registers, one point per warp at a time),
  * 2 = ring kernels (rows staged in shared memory by async copies across point boundaries, softmax
  * statistics one lane per point; need G == 4 and rows of whole 16-byte chunks, <= 512 bytes --
- * anything else runs on the streaming kernels whatever the setting). */
+ * anything else runs on the streaming kernels whatever the setting), 3 = backward on the
+ * lane-per-view kernel (groups of <= 32 views per warp: lane per view for the scores, sub-warp per
+ * row for the features; G == 4, rows of 4 / 8 / 16 / 32 chunks), forward as in auto.
+ * TEST / TUNING ONLY: production callers leave it at 0; the choice is a pure function of the shape. */
 int dva_view_attention_set_path(int path);
 
 /* Backward of the chain above.

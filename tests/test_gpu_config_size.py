@@ -21,11 +21,11 @@ pytestmark = pytest.mark.gpu
 CONFIGS = {"config1_s3dis": dict(N=160_000, mean_v=8, C=64), "config3_kitti360": dict(N=80_000, mean_v=20, C=128)}
 
 
-@pytest.fixture(params=["auto", "stream", "ring"])
+@pytest.fixture(params=["auto", "stream", "ring", "lane"])
 def path(request):
     from deepviewagg_b200 import _lib
     lib = _lib.load()
-    assert lib.dva_view_attention_set_path({"auto": 0, "stream": 1, "ring": 2}[request.param]) == 0
+    assert lib.dva_view_attention_set_path({"auto": 0, "stream": 1, "ring": 2, "lane": 3}[request.param]) == 0
     yield request.param
     assert lib.dva_view_attention_set_path(0) == 0
 

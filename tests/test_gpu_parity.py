@@ -95,13 +95,13 @@ def test_segment_edge_cases():
         ops.segment_csr(big, torch.tensor([0, 100000], dtype=torch.int32).cuda())
 
 
-@pytest.fixture(params=["stream", "ring"])
+@pytest.fixture(params=["stream", "ring", "lane"])
 def va_path(request):
-    """Run the test once per implementation of the fused pair (streaming kernels / ring kernels,
-    dva_view_attention_set_path); the default 'auto' choice is restored afterwards."""
+    """Run the test once per implementation of the fused pair (streaming kernels / ring kernels /
+    lane-per-view backward, dva_view_attention_set_path); the default 'auto' choice is restored afterwards."""
     from deepviewagg_b200 import _lib
     lib = _lib.load()
-    assert lib.dva_view_attention_set_path({"stream": 1, "ring": 2}[request.param]) == 0
+    assert lib.dva_view_attention_set_path({"stream": 1, "ring": 2, "lane": 3}[request.param]) == 0
     yield request.param
     assert lib.dva_view_attention_set_path(0) == 0
 

@@ -54,11 +54,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--groups", type=int, default=4)
     ap.add_argument("--out", default="")
-    ap.add_argument("--path", default="auto", choices=["auto", "stream", "ring"])
+    ap.add_argument("--path", default="auto", choices=["auto", "stream", "ring", "lane"])
     args = ap.parse_args()
     from deepviewagg_b200.host_api import ViewAttentionHostPlan
     from deepviewagg_b200 import _lib
-    assert _lib.load().dva_view_attention_set_path({"auto": 0, "stream": 1, "ring": 2}[args.path]) == 0
+    assert _lib.load().dva_view_attention_set_path({"auto": 0, "stream": 1, "ring": 2, "lane": 3}[args.path]) == 0
     try:
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
