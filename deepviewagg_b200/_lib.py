@@ -57,6 +57,7 @@ SIGNATURES = {
                             _vp, _vp, _vp]),
     "dva_neighborhood_features": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _f64, _i32, _i32, _vp,
                                          _i64, _i64, _vp]),
+    "dva_scatter_add_rows": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp]),
     "dva_mapping_build_workspace_bytes": (_sz, [_i64, _i64]),
     "dva_mapping_build": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _vp, _vp, _sz, _vp]),

@@ -372,7 +372,7 @@ class ImageMapping(CSRData):
         """image.py:2279-2342."""
         ap = self.values[1].pointers
         image_ids = _expand(self.images, ap)
-        pixels = self.pixels - crop_offsets.to(self.device)[image_ids].to(self.pixels.dtype)
+        pixels = self.pixels - crop_offsets.to(self.device)[image_ids]     # promotes to the offsets' dtype (int64), like image.py:2302
         size = torch.tensor(crop_size, device=self.device)
         inside = torch.where((pixels >= 0).all(dim=1) & (pixels < size).all(dim=1))[0]
         if inside.shape[0] == 0:

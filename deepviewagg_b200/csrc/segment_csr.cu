@@ -222,6 +222,31 @@ pick_rows_kernel(const T* __restrict__ x, const int64_t* __restrict__ arg, T* __
   }
 }
 
+// ---- rows scatter-add: dst[idx[v], :] += src[v, :]  (dst fp32, pre-zeroed by the caller) --------------
+// backward of a row gather x[idx] with repeated rows (a caller-supplied row_index that is not a
+// permutation, pooling.py `x_mod[idx]`), and of HeuristicBimodalCSRPool's row pick (pooling.py:146-150;
+// idx[i] == n_rows marks "no view": skipped).  red.global.add.v4.f32: one instruction per four channels.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+scatter_add_rows_kernel(const T* __restrict__ src, const int64_t* __restrict__ idx, float* __restrict__ dst,
+                        int64_t V, int64_t R, int64_t C) {
+  const int64_t CV = C / VEC, total = V * CV;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = t / CV, cv = t - v * CV;
+    const int64_t r = idx[v];
+    if (r < 0 || r >= R) continue;
+    float f[VEC];
+    if constexpr (VEC == 1) { f[0] = Cvt<T>::to_f(src[v * C + cv]); atomicAdd(dst + r * C + cv, f[0]); }
+    else {
+      unpack16<T, VEC>(*reinterpret_cast<const uint4*>(src + v * C + cv * VEC), f);
+      float* d = dst + r * C + cv * VEC;
+#pragma unroll
+      for (int j = 0; j < VEC; j += 4)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + j), "f"(f[j]), "f"(f[j + 1]), "f"(f[j + 2]), "f"(f[j + 3]) : "memory");
+    }
+  }
+}
+
 // ---- host-side dispatch ---------------------------------------------------------------------
 static inline int grid_for(int64_t total, int threads = 256) {
   int64_t blocks = (total + threads - 1) / threads;
@@ -399,6 +424,24 @@ extern "C" int dva_heuristic_pool_fwd(const void* x_mod, const float* x_map, int
       pick_rows_kernel<T, 1><<<grid_for(N * C), 256, 0, st>>>((const T*)x_mod, arg, (T*)out, N, V, C);
     }
     return check_launch("pick_rows");
+  });
+  return DVA_OK;
+}
+
+extern "C" int dva_scatter_add_rows(const void* src, const int64_t* idx, float* dst, int64_t V, int64_t R,
+                                    int64_t C, int dtype, void* stream) {
+  if (V < 0 || R < 0 || C < 0) return fail(DVA_EINVAL, "scatter_add_rows: negative size");
+  if (V == 0 || C == 0) return DVA_OK;
+  if (!src || !idx || !dst) return fail(DVA_EINVAL, "scatter_add_rows: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  DVA_DISPATCH_DTYPE(dtype, {
+    constexpr int VEC = Vec16<T>::N;
+    if (C % VEC == 0 && aligned16(src) && aligned16(dst)) {
+      scatter_add_rows_kernel<T, VEC><<<grid_for(V * (C / VEC)), 256, 0, st>>>((const T*)src, idx, dst, V, R, C);
+    } else {
+      scatter_add_rows_kernel<T, 1><<<grid_for(V * C), 256, 0, st>>>((const T*)src, idx, dst, V, R, C);
+    }
+    return check_launch("scatter_add_rows");
   });
   return DVA_OK;
 }

@@ -751,6 +751,8 @@ extern "C" int dva_view_attention_fwd(const void* x, const void* idx, int idx_is
   P.N = N; P.V = V; P.R = R; P.C = (int)C; P.G = (int)G; P.group_scaling = group_scaling; P.eps = eps;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype != DVA_F32 && dtype != DVA_BF16 && dtype != DVA_F16) return fail(DVA_EINVAL, "view_attention_fwd: unknown dtype");
+  // path 3 pins the lane-per-view forward; auto keeps the ring forward for short segments until measured otherwise
+  if (va_path().load(std::memory_order_relaxed) == 3 && va_lane_fwd_applicable(P, dtype)) return va_lane_fwd(P, dtype, st);
   if (use_ring(P, dtype, va_ring_fwd_applicable(P, dtype), false)) return va_ring_fwd(P, dtype, st);
   switch (dtype) {
     case DVA_F32: return fwd_typed<float>(P, st);
@@ -761,7 +763,7 @@ extern "C" int dva_view_attention_fwd(const void* x, const void* idx, int idx_is
 }
 
 extern "C" int dva_view_attention_set_path(int path) {
-  if (path < 0 || path > 3) return fail(DVA_EINVAL, "view_attention_set_path: 0 = auto, 1 = streaming, 2 = ring, 3 = lane (backward)");
+  if (path < 0 || path > 3) return fail(DVA_EINVAL, "view_attention_set_path: 0 = auto, 1 = streaming, 2 = ring, 3 = lane");
   va_path().store(path, std::memory_order_relaxed);
   return DVA_OK;
 }

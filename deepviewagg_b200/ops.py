@@ -227,6 +227,18 @@ def segment_softmax_csr(src, csr_idx, eps=1e-12, scaling=False):
 # --------------------------------------------------------------------------------------------
 # fused view attention (modules.py:518 + pooling.py:285-300 / 515-530)
 # --------------------------------------------------------------------------------------------
+def _scatter_add_rows(src, idx, n_rows):
+    """fp32 [n_rows, C] with dst[idx[v]] += src[v] (dva_scatter_add_rows)."""
+    lib = _lib.load()
+    src = src.contiguous()
+    V, C = src.shape
+    dst = torch.zeros((n_rows, C), dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        check(lib.dva_scatter_add_rows(ptr(src), ptr(idx.contiguous()), ptr(dst), V, n_rows, C, dtype_code(src),
+                                       stream_ptr()), "dva_scatter_add_rows")
+    return dst
+
+
 def fused_groups_supported(num_groups):
     return 1 <= num_groups <= 32 and (num_groups & (num_groups - 1)) == 0
 
@@ -300,8 +312,8 @@ class _ViewAttention(torch.autograd.Function):
                                              ws_bytes, stream_ptr()), "dva_view_attention_bwd")
         if idx is None or scatter:
             gx = gx_rows
-        else:  # general (non-injective) gather: accumulate duplicated rows
-            gx = torch.zeros((R, C), dtype=x.dtype, device=x.device).index_add_(0, idx.long(), gx_rows)
+        else:  # general (non-injective) gather: accumulate duplicated rows (red.global.add.v4.f32 kernel)
+            gx = _scatter_add_rows(gx_rows, idx.long(), R).to(x.dtype)
         g_w = ggate[0].view(w_shape).to(w_dtype) if gw is not None else None
         g_b = ggate[1].view(b_shape).to(w_dtype) if gw is not None else None
         return gx, None, gcompat, None, g_w, g_b, None, None, None, None
@@ -399,10 +411,9 @@ class _HeuristicPool(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
         (arg,) = ctx.saved_tensors
-        # each point picks a distinct view (or none): a plain row scatter, no accumulation
-        g = torch.zeros((ctx.V + 1, grad_out.shape[1]), dtype=grad_out.dtype, device=grad_out.device)
-        g.index_copy_(0, arg, grad_out.contiguous())
-        return g[:ctx.V], None, None, None, None
+        # each point picks a distinct view (arg == V: none, skipped by the kernel)
+        g = _scatter_add_rows(grad_out.contiguous(), arg, ctx.V).to(grad_out.dtype)
+        return g, None, None, None, None
 
 
 def heuristic_pool(x_mod, x_map, csr_idx, feat, mode="max"):

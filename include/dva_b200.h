@@ -327,6 +327,13 @@ int dva_project_camera(const float* xyz, const float* cam, int camera, float* di
                        double* y_proj, uint8_t* keep, int64_t n, int64_t W, int64_t H,
                        int64_t crop_top, int64_t crop_bottom, float r_min, float r_max, void* stream);
 
+/* rows scatter-add: dst[idx[v], :] += src[v, :] for v < V; dst [R, C] fp32 must be zero-initialised by the
+ * caller; rows with idx outside [0, R) are skipped.  Backward of `x_mod[row_index]` when row_index repeats
+ * rows (modules.py:518 with a caller-supplied index) and of HeuristicBimodalCSRPool's row pick
+ * (pooling.py:146-150, "no view" = index V). */
+int dva_scatter_add_rows(const void* src, const int64_t* idx, float* dst, int64_t V, int64_t R, int64_t C,
+                         int dtype, void* stream);
+
 /* I1 / I4 / I6  native construction of the point -> view -> pixel CSR (csrc/mapping_build.cu)
  *   replaces ImageMapping.from_dense image.py:1728-1795 (lexargsort + unique + cumsum chains) and the
  *   dense expansion / lexargunique / scatter_mean / from_dense sequence of select_points('merge')

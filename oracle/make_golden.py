@@ -197,6 +197,7 @@ def main():
     make_camera_golden(ref)
     make_visibility_model_golden(ref)
     make_block_down_golden(ref)
+    make_image_ops_golden(ref)
 
 
 def make_camera_golden(ref):
@@ -481,6 +482,53 @@ def make_block_down_golden(ref):
     arrays["merge_x_seen"] = d["x_seen"] > 0 if d["x_seen"].dtype != torch.bool else d["x_seen"]
     arrays.update(_dump_mappings(d["modalities"]["image"], "merge_"))
     save("block_down", **arrays)
+
+
+def make_image_ops_golden(ref):
+    """I3 / I4: ImageMapping.select_images (image.py:2029-2093), select_views (:2095-2165), crop (:2279-2342),
+    downscale_images / upscale_images (:1916-2027) executed on the mapping of the image_mapping fixture."""
+    lex, image = ref.lex, ref.image
+    gen = torch.Generator().manual_seed(77)                  # same inputs as make_integer_golden
+    n_points, n_items = 500, 4000
+    pid = torch.randint(0, n_points, (n_items,), generator=gen)
+    iid = torch.randint(0, 5, (n_items,), generator=gen)
+    pix = torch.randint(0, 64, (n_items, 2), generator=gen).short()
+    feat = torch.rand(n_items, 3, generator=gen)
+    keep = lex.lexargunique(pid, iid, pix[:, 0].long(), pix[:, 1].long())
+    pid, iid, pix, feat = pid[keep], iid[keep], pix[keep], feat[keep]
+    # a FRESH mapping per operation: the reference's clone() is shallow (csr.py:147-156) and upscale_images
+    # writes into the nested pixel CSR it shares with the original (image.py:2024), so results would depend on
+    # the order of the calls
+    fresh = lambda: image.ImageMapping.from_dense(pid.clone(), iid.clone(), pix.clone(), feat.clone(),  # noqa: E731
+                                                  num_points=n_points + 7)
+    m = fresh()
+    gen2 = torch.Generator().manual_seed(99)
+    arrays = dict(point_ids=pid, image_ids=iid, pixels=pix, features=feat, num_points=np.array(n_points + 7))
+
+    def dump(tag, mm):
+        arrays[f"{tag}_pointers"] = mm.pointers
+        arrays[f"{tag}_images"] = mm.images
+        arrays[f"{tag}_atomic_pointers"] = mm.values[1].pointers
+        arrays[f"{tag}_pixels"] = mm.pixels
+        arrays[f"{tag}_features"] = mm.features
+
+    img_idx = torch.tensor([3, 0, 4])
+    arrays["img_idx"] = img_idx
+    dump("select_images", fresh().select_images(img_idx))
+    view_mask = (torch.rand(m.num_items, generator=gen2) < 0.6) & (m.images != 2)   # image 2 disappears: renumbering
+    arrays["view_mask"] = view_mask
+    mv, seen_images = fresh().select_views(view_mask)               # (mapping, indices of the images still seen)
+    arrays["select_views_img_idx"] = seen_images
+    dump("select_views", mv)
+    crop_size = (40, 32)
+    crop_offsets = torch.tensor([[3, 5], [10, 0], [0, 20], [24, 30], [7, 7]])
+    arrays["crop_size"] = np.array(crop_size)
+    arrays["crop_offsets"] = crop_offsets
+    dump("crop", fresh().crop(crop_size, crop_offsets))
+    dump("down4", fresh().downscale_images(4))
+    dump("up2", fresh().upscale_images(2))
+    dump("up2_nocenter", fresh().upscale_images(2, center=False))
+    save("image_ops", **arrays)
 
 
 def make_interp_golden(ref):
