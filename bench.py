@@ -78,6 +78,8 @@ def parse():
     p.add_argument("--idx", default="randperm", choices=["randperm", "arange", "none"])
     p.add_argument("--counts", default="uniform", choices=["uniform", "ragged"])
     p.add_argument("--rounds", type=int, default=0, help="timed repetitions of the K-step region (0 = from a 2.5 s budget)")
+    p.add_argument("--sweep", default="", help="comma list of views per point (BASELINE config #5: 8,16,32,64): extra "
+                                               "device-resident measurements under roofline_detail.sweep")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-modules", action="store_true", help="skip the whole-module side measurements (roofline_detail.modules)")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -504,6 +506,8 @@ def main():
     if not args.no_e2e:
         e2e = run_e2e(args, plan, dist, dev, world, N, V, n_bucket)
 
+    if rank == 0 and world == 1 and args.sweep:
+        extra_roof["sweep"] = run_sweep(args, dev, peak, [int(t) for t in args.sweep.split(",") if t])
     if rank == 0 and world == 1 and not args.no_modules:
         try:
             extra_roof["modules"] = run_module_workloads(dev, peak)
@@ -594,6 +598,43 @@ def run_module_workloads(dev, peak, steps=20, warmup=5):
                      "frac": bytes_ / (ms * 1e-3) / 1e9 / peak, "steps": steps,
                      "what": "GroupBimodalCSRPool(use_mod=False, DeepSetFeat, use_num) train step, fwd + bwd, fp32"}
         del m, x_mod, x_map, w
+    return out
+
+
+def run_sweep(args, dev, peak, views_list, steps=10, warmup=3):
+    """BASELINE.json config #5: the same fused pair at N points x v views for every v of the sweep (uniform counts,
+    random permutation), device-resident, median over `steps` launches."""
+    from deepviewagg_b200.host_api import ViewAttentionHostPlan
+    tdtype = torch.float32 if args.dtype == "f32" else torch.bfloat16
+    s = 4 if args.dtype == "f32" else 2
+    N, C, G = args.points, args.channels, args.groups
+    out = {}
+    for v in views_list:
+        V = N * v
+        gen = torch.Generator(device=dev).manual_seed(99 + v)
+        plan = ViewAttentionHostPlan(N, V, V, C, G, dtype=tdtype, idx_dtype=torch.int32, gating=True, group_scaling=True,
+                                     device=dev)
+        plan.ptr.copy_(torch.arange(0, V + 1, v, device=dev))
+        plan.x.copy_(torch.randn(V, C, device=dev, generator=gen).to(tdtype))
+        plan.idx.copy_(torch.randperm(V, device=dev, generator=gen).int())
+        plan.compat.copy_(torch.randn(V, G, device=dev, generator=gen))
+        plan.gate[0].fill_(1.0)
+        plan.gate[1].fill_(0.0)
+        plan.gout.copy_(torch.randn(N, C, device=dev, generator=gen).to(tdtype))
+        fw, bw = [], []
+        for i in range(warmup + steps):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record(); plan.forward_device(); e[1].record(); plan.backward_device(); e[2].record()
+            torch.cuda.synchronize()
+            if i >= warmup:
+                fw.append(e[0].elapsed_time(e[1])); bw.append(e[1].elapsed_time(e[2]))
+        f_ms, b_ms = statistics.median(fw), statistics.median(bw)
+        bf, bb = algorithmic_bytes(N, V, C, G, s)
+        out[str(v)] = {"fwd_ms": f_ms, "bwd_ms": b_ms, "mpoints_per_s": N / (f_ms + b_ms) / 1e3,
+                       "fwd_frac": bf / (f_ms * 1e-3) / 1e9 / peak, "bwd_frac": bb / (b_ms * 1e-3) / 1e9 / peak,
+                       "step_frac": (bf + bb) / ((f_ms + b_ms) * 1e-3) / 1e9 / peak}
+        del plan
+        torch.cuda.empty_cache()
     return out
 
 

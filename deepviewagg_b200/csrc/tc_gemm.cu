@@ -792,8 +792,11 @@ extern "C" size_t dva_linear_bnstats_workspace_bytes(int64_t n_out, int64_t k_re
   return dva_tc_rows_workspace_bytes(n_out, k_red) + (size_t)kNumSMs * 3 * tc::kTile * 4;
 }
 
+extern "C" int dva_tc_narrow();
 extern "C" int dva_linear_bnstats_supported(int64_t M, int64_t n_out, int64_t k_red) {
-  return dva_tc_rows_supported(M, n_out, k_red) && n_out <= tc::kTile && n_out % 4 == 0 && n_out > 32 && k_red > 32;
+  if (!(dva_tc_rows_supported(M, n_out, k_red) && n_out <= tc::kTile && n_out % 4 == 0)) return 0;
+  if (dva_tc_narrow()) return n_out >= 32 && k_red >= 8;
+  return n_out > 32 && k_red > 32;
 }
 
 extern "C" int dva_linear_bnstats_fwd(const float* X, const float* W, float* D, int64_t M, int64_t n_out,

@@ -715,12 +715,15 @@ static bool use_ring(const VAParams& P, int dtype, bool applicable, bool backwar
 }
 
 // backward only: the lane-per-view kernel (view_attention_lane.cu) for short segments, path 3 forces it
-static bool use_lane_bwd(const VAParams& P, bool applicable) {
+// auto (profiles/r2_shapes_*.json): short segments AND rows of at most 256 bytes -- with 512-byte rows the
+// streaming backward is as fast (1 M x 8 x 128: 1.85 ms vs 1.99 ms)
+static bool use_lane_bwd(const VAParams& P, int dtype, bool applicable) {
   if (!applicable) return false;
   const int path = va_path().load(std::memory_order_relaxed);
   if (path == 3) return true;
   if (path != 0) return false;
-  return P.V <= (int64_t)DVA_RING_MAX_MEAN_VIEWS * P.N;
+  const size_t esz = dtype == DVA_F32 ? 4 : 2;
+  return P.V <= (int64_t)DVA_RING_MAX_MEAN_VIEWS * P.N && (size_t)P.C * esz <= 256;
 }
 
 }  // namespace dva
@@ -751,8 +754,6 @@ extern "C" int dva_view_attention_fwd(const void* x, const void* idx, int idx_is
   P.N = N; P.V = V; P.R = R; P.C = (int)C; P.G = (int)G; P.group_scaling = group_scaling; P.eps = eps;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype != DVA_F32 && dtype != DVA_BF16 && dtype != DVA_F16) return fail(DVA_EINVAL, "view_attention_fwd: unknown dtype");
-  // path 3 pins the lane-per-view forward; auto keeps the ring forward for short segments until measured otherwise
-  if (va_path().load(std::memory_order_relaxed) == 3 && va_lane_fwd_applicable(P, dtype)) return va_lane_fwd(P, dtype, st);
   if (use_ring(P, dtype, va_ring_fwd_applicable(P, dtype), false)) return va_ring_fwd(P, dtype, st);
   switch (dtype) {
     case DVA_F32: return fwd_typed<float>(P, st);
@@ -763,7 +764,7 @@ extern "C" int dva_view_attention_fwd(const void* x, const void* idx, int idx_is
 }
 
 extern "C" int dva_view_attention_set_path(int path) {
-  if (path < 0 || path > 3) return fail(DVA_EINVAL, "view_attention_set_path: 0 = auto, 1 = streaming, 2 = ring, 3 = lane");
+  if (path < 0 || path > 3) return fail(DVA_EINVAL, "view_attention_set_path: 0 = auto, 1 = streaming, 2 = ring, 3 = lane (backward)");
   va_path().store(path, std::memory_order_relaxed);
   return DVA_OK;
 }
@@ -807,7 +808,7 @@ extern "C" int dva_view_attention_bwd(const void* x, const void* idx, int idx_is
   int grid = 1;
   int rc;
   if (dtype != DVA_F32 && dtype != DVA_BF16 && dtype != DVA_F16) return fail(DVA_EINVAL, "view_attention_bwd: unknown dtype");
-  if (use_lane_bwd(P, va_lane_bwd_applicable(P, dtype))) {
+  if (use_lane_bwd(P, dtype, va_lane_bwd_applicable(P, dtype))) {
     rc = va_lane_bwd(P, dtype, &grid, st);
   } else if (use_ring(P, dtype, va_ring_bwd_applicable(P, dtype), true)) {
     rc = va_ring_bwd(P, dtype, &grid, st);

@@ -39,8 +39,6 @@ int va_ring_fwd(const VAParams& P, int dtype, cudaStream_t st);
 int va_ring_bwd(const VAParams& P, int dtype, int* grid_out, cudaStream_t st);
 
 // lane-per-view backward for short segments (view_attention_lane.cu)
-bool va_lane_fwd_applicable(const VAParams& P, int dtype);
-int va_lane_fwd(const VAParams& P, int dtype, cudaStream_t st);
 bool va_lane_bwd_applicable(const VAParams& P, int dtype);
 int va_lane_bwd(const VAParams& P, int dtype, int* grid_out, cudaStream_t st);
 

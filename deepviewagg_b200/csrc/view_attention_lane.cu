@@ -12,8 +12,11 @@
 //            per instruction; coalesced 16-byte score loads);
 //   phase 1b EVERY VIEW LANE issues ONE bulk async copy (cp.async.bulk -> UBLKCP) of its own row into the
 //            warp's shared-memory row buffer, completion on the warp's mbarrier: up to 32 rows in flight per
-//            warp for one instruction slot each and no registers -- what keeps ~150 KB in flight per SM (the
-//            register-only first version had 40 KB in flight and sat at 0.54 of the peak, latency-bound);
+//            warp for one instruction slot each and no registers (the register-only first version had 40 KB
+//            in flight per SM and sat at 0.54 of the peak, latency-bound; this one 0.63 / 0.76 at 160 k / 1 M
+//            points x 7 views x 64 ch).  Tried and dropped: a second row buffer with the next group's copies
+//            issued one group ahead -- twice the shared memory (12 instead of 20 warps per SM) and fewer
+//            rows per step in flight made it 1.8x SLOWER;
 //   phase 2  SUB-WARP PER ROW: LPR lanes own the 16-byte chunks of a row, 32 / LPR rows per step: x row out
 //            of shared memory (LDS.128), grad_out row of the view's point through L1; dx = (a t) grad_out
 //            stored once, raw dot <grad_out, x> per group to a tile;
@@ -358,303 +361,6 @@ va_lane_bwd_kernel(const VAParams P, const int PR) {
       for (int w = 0; w < kLaneWarps; ++w) acc += gate_s[w][threadIdx.x];
       P.gate_partial[(int64_t)blockIdx.x * 2 * G + threadIdx.x] = acc;
     }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// forward twin: same group structure and bulk-copied rows.
-//   phase 1  lane per VIEW: row copy issued, scores -> tile;  lane per POINT: max / first arg-max / denominator /
-//            gate over its (few) views out of the tile, e-values back into the tile, saved statistics;
-//            lane per VIEW: attentions stored as one coalesced float4 per lane;
-//   phase 2  SUB-WARP PER POINT: LPR lanes own the chunks of the point's output row and walk its rows in
-//            shared memory (LDS.128 + LDS weight + VEC FFMA per row), output row stored once (zeros if unseen).
-// ---------------------------------------------------------------------------------------------------------
-template <typename T, int LPR>
-__global__ void __launch_bounds__(kLaneWarps * 32, 6)
-va_lane_fwd_kernel(const VAParams P, const int PR) {
-  constexpr int VEC = Vec16<T>::N, RPI = 32 / LPR, CPE = LPR / 4, RS = LPR * 16;
-  extern __shared__ __align__(128) unsigned char rows_all[];
-  __shared__ LaneSmem sm_all[kLaneWarps];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  LaneSmem& sm = sm_all[warp];
-  unsigned char* rows_s = rows_all + (size_t)warp * 32 * RS;
-  const uint32_t rows_u = lane_smem_u32(rows_s), bar_u = lane_smem_u32(&sm.bar);
-  uint32_t uses = 0;
-  if (lane == 0) {
-    lane_mbar_init(bar_u, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-  const int sg = lane / LPR, lir = lane % LPR, gk = lir / CPE;
-  const uint32_t row_bytes = (uint32_t)P.C * sizeof(T);
-  const char* __restrict__ xbase = reinterpret_cast<const char*>(P.x);
-  char* __restrict__ ob = reinterpret_cast<char*>(P.out) + lir * 16;
-  const bool gating = P.gate_w != nullptr, save = P.seg_max != nullptr;
-  float4 gw4 = make_float4(0.f, 0.f, 0.f, 0.f), gb4 = gw4;
-  if (gating) {
-    gw4 = make_float4(P.gate_w[0], P.gate_w[1], P.gate_w[2], P.gate_w[3]);
-    gb4 = make_float4(P.gate_b[0], P.gate_b[1], P.gate_b[2], P.gate_b[3]);
-  }
-  auto issue_rows = [&](int nv, uint32_t rid) {
-    lane_fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) lane_mbar_expect_tx(bar_u, (uint32_t)nv * row_bytes);
-    __syncwarp();
-    if (lane < nv) lane_bulk_g2s(rows_u + (uint32_t)lane * RS, xbase + (uint64_t)rid * row_bytes, row_bytes, bar_u);
-  };
-  auto wait_rows = [&]() { lane_mbar_wait(bar_u, uses & 1u); ++uses; };
-
-  const int64_t n_ranges = (P.N + PR - 1) / PR;
-  const int64_t warps_total = (int64_t)gridDim.x * kLaneWarps;
-  for (int64_t r = (int64_t)blockIdx.x * kLaneWarps + warp; r < n_ranges; r += warps_total) {
-    const int64_t pa = r * PR;
-    const int64_t pb = (pa + PR < P.N) ? pa + PR : P.N;
-    for (int64_t pg = pa; pg < pb;) {
-      const int64_t pk = pg + lane;
-      const bool valid = pk < pb;
-      const int64_t p0 = valid ? P.ptr[pk] : 0;
-      const int cnt = valid ? (int)(P.ptr[pk + 1] - p0) : 0;
-      int incl = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(kFull, incl, o);
-        if (lane >= o) incl += t;
-      }
-      const int excl = incl - cnt;
-      const unsigned fitm = __ballot_sync(kFull, valid && incl <= 32);
-      const int kfit = (fitm == kFull) ? 32 : __ffs(~fitm) - 1;
-      const int64_t gvb = __shfl_sync(kFull, p0, 0);
-
-      if (kfit == 0) {
-        // ---- one point with more than 32 views: statistics over all scores first, then chunks of 32 rows
-        const int n = __shfl_sync(kFull, cnt, 0);
-        const float inv_sq = P.group_scaling ? rsqrtf((float)n) : 1.f;
-        const float4* __restrict__ cp = reinterpret_cast<const float4*>(P.compat) + gvb;
-        float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        int4 ar = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff);
-        for (int j = lane; j < n; j += 32) {
-          const float4 c = __ldg(cp + j);
-          if (c.x > mx.x) { mx.x = c.x; ar.x = j; }
-          if (c.y > mx.y) { mx.y = c.y; ar.y = j; }
-          if (c.z > mx.z) { mx.z = c.z; ar.z = j; }
-          if (c.w > mx.w) { mx.w = c.w; ar.w = j; }
-        }
-#define DVA_LMAX(c)                                                                      \
-        for (int o = 16; o > 0; o >>= 1) {                                               \
-          const float om = __shfl_xor_sync(kFull, mx.c, o);                              \
-          const int oa = __shfl_xor_sync(kFull, ar.c, o);                                \
-          if (om > mx.c || (om == mx.c && oa < ar.c)) { mx.c = om; ar.c = oa; }          \
-        }
-        DVA_LMAX(x) DVA_LMAX(y) DVA_LMAX(z) DVA_LMAX(w)
-#undef DVA_LMAX
-        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int j = lane; j < n; j += 32) {
-          const float4 c = __ldg(cp + j);
-          d.x += __expf((c.x - mx.x) * inv_sq); d.y += __expf((c.y - mx.y) * inv_sq);
-          d.z += __expf((c.z - mx.z) * inv_sq); d.w += __expf((c.w - mx.w) * inv_sq);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          d.x += __shfl_xor_sync(kFull, d.x, o); d.y += __shfl_xor_sync(kFull, d.y, o);
-          d.z += __shfl_xor_sync(kFull, d.z, o); d.w += __shfl_xor_sync(kFull, d.w, o);
-        }
-        const float4 dn = make_float4(d.x + P.eps, d.y + P.eps, d.z + P.eps, d.w + P.eps);
-        float4 sc = make_float4(1.f / dn.x, 1.f / dn.y, 1.f / dn.z, 1.f / dn.w);
-        if (save && lane == 0) {
-          reinterpret_cast<float4*>(P.seg_max)[pg] = mx;
-          reinterpret_cast<float4*>(P.seg_den)[pg] = dn;
-          reinterpret_cast<int4*>(P.seg_arg)[pg] = make_int4((int)gvb + ar.x, (int)gvb + ar.y, (int)gvb + ar.z, (int)gvb + ar.w);
-        }
-        float4 sct = sc;
-        if (gating) {
-          sct.x *= tanhf(fmaxf(fmaf(gw4.x, mx.x, gb4.x), 0.f)); sct.y *= tanhf(fmaxf(fmaf(gw4.y, mx.y, gb4.y), 0.f));
-          sct.z *= tanhf(fmaxf(fmaf(gw4.z, mx.z, gb4.z), 0.f)); sct.w *= tanhf(fmaxf(fmaf(gw4.w, mx.w, gb4.w), 0.f));
-        }
-        float acc[VEC];
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
-        for (int c0 = 0; c0 < n; c0 += 32) {
-          const int nv = (n - c0 < 32) ? n - c0 : 32;
-          const int64_t v = gvb + c0 + lane;
-          __syncwarp();
-          const uint32_t rid = lane < nv ? lane_row_id(P.idx, P.idx64, v) : 0u;
-          issue_rows(nv, rid);
-          if (lane < nv) {
-            const float4 c = __ldg(cp + c0 + lane);
-            const float4 e = make_float4(__expf((c.x - mx.x) * inv_sq), __expf((c.y - mx.y) * inv_sq),
-                                         __expf((c.z - mx.z) * inv_sq), __expf((c.w - mx.w) * inv_sq));
-            *reinterpret_cast<float4*>(sm.wt[lane]) = e;
-            if (P.att != nullptr)
-              reinterpret_cast<float4*>(P.att)[v] = make_float4(e.x * sc.x, e.y * sc.y, e.z * sc.z, e.w * sc.w);
-          }
-          __syncwarp();
-          wait_rows();
-          for (int u = sg; u < nv; u += RPI) {
-            float fx[VEC];
-            unpack16<T, VEC>(*reinterpret_cast<const uint4*>(rows_s + (size_t)u * RS + lir * 16), fx);
-            const float e = sm.wt[u][gk];
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) acc[j] = fmaf(e, fx[j], acc[j]);
-          }
-        }
-        const float scale = pick4(sct, gk);
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-          float a = acc[j];
-#pragma unroll
-          for (int o = LPR; o < 32; o <<= 1) a += __shfl_xor_sync(kFull, a, o);
-          acc[j] = a * scale;
-        }
-        if (sg == 0) stg_stream16(ob + pg * (int64_t)row_bytes, pack16<T, VEC>(acc));
-        pg += 1;
-        continue;
-      }
-
-      // ---- phase 1a: lane per view
-      const int nv = __shfl_sync(kFull, incl, kfit - 1);
-      const int64_t v = gvb + lane;
-      __syncwarp();                                                 // previous group's tiles are free
-      const uint32_t rid = lane < nv ? lane_row_id(P.idx, P.idx64, v) : 0u;
-      if (nv > 0) issue_rows(nv, rid);
-      if (lane < nv) *reinterpret_cast<float4*>(sm.wt[lane]) = __ldg(reinterpret_cast<const float4*>(P.compat) + v);
-      sm.ri[lane] = (uint32_t)excl;                                 // first view / number of views of point pg + lane
-      sm.go[lane] = (uint32_t)cnt;
-      __syncwarp();
-      // ---- phase 1b: lane per point
-      if (lane < kfit) {
-        float4 mx = make_float4(0.f, 0.f, 0.f, 0.f), dn = make_float4(P.eps, P.eps, P.eps, P.eps);
-        float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sct = sc;
-        int4 ar = make_int4(-1, -1, -1, -1);
-        if (cnt > 0) {
-          mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-          int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-          for (int j = 0; j < cnt; ++j) {
-            const float4 c = *reinterpret_cast<const float4*>(sm.wt[excl + j]);
-            if (c.x > mx.x) { mx.x = c.x; a0 = j; }
-            if (c.y > mx.y) { mx.y = c.y; a1 = j; }
-            if (c.z > mx.z) { mx.z = c.z; a2 = j; }
-            if (c.w > mx.w) { mx.w = c.w; a3 = j; }
-          }
-          const int v0g = (int)(gvb + excl);
-          ar = make_int4(v0g + a0, v0g + a1, v0g + a2, v0g + a3);
-          const float inv_sq = P.group_scaling ? rsqrtf((float)cnt) : 1.f;
-          float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int j = 0; j < cnt; ++j) {
-            float4* w = reinterpret_cast<float4*>(sm.wt[excl + j]);
-            const float4 c = *w;
-            const float4 e = make_float4(__expf((c.x - mx.x) * inv_sq), __expf((c.y - mx.y) * inv_sq),
-                                         __expf((c.z - mx.z) * inv_sq), __expf((c.w - mx.w) * inv_sq));
-            d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w;
-            *w = e;
-          }
-          dn = make_float4(d.x + P.eps, d.y + P.eps, d.z + P.eps, d.w + P.eps);
-          sc = make_float4(1.f / dn.x, 1.f / dn.y, 1.f / dn.z, 1.f / dn.w);
-          sct = sc;
-          if (gating) {
-            sct.x *= tanhf(fmaxf(fmaf(gw4.x, mx.x, gb4.x), 0.f)); sct.y *= tanhf(fmaxf(fmaf(gw4.y, mx.y, gb4.y), 0.f));
-            sct.z *= tanhf(fmaxf(fmaf(gw4.z, mx.z, gb4.z), 0.f)); sct.w *= tanhf(fmaxf(fmaf(gw4.w, mx.w, gb4.w), 0.f));
-          }
-        }
-        if (save) {
-          reinterpret_cast<float4*>(P.seg_max)[pk] = mx;
-          reinterpret_cast<float4*>(P.seg_den)[pk] = dn;
-          reinterpret_cast<int4*>(P.seg_arg)[pk] = ar;
-        }
-        *reinterpret_cast<float4*>(sm.Sp[lane]) = sc;
-        *reinterpret_cast<float4*>(sm.dq[lane]) = sct;
-      }
-      __syncwarp();
-      // ---- phase 1c: lane per view: attentions
-      if (P.att != nullptr && lane < nv) {
-        int mp = 0;
-        for (int k = 0; k < kfit; ++k)
-          if ((uint32_t)lane >= sm.ri[k] && (uint32_t)lane < sm.ri[k] + sm.go[k]) mp = k;
-        const float4 e = *reinterpret_cast<const float4*>(sm.wt[lane]);
-        const float4 sc = *reinterpret_cast<const float4*>(sm.Sp[mp]);
-        reinterpret_cast<float4*>(P.att)[v] = make_float4(e.x * sc.x, e.y * sc.y, e.z * sc.z, e.w * sc.w);
-      }
-      // ---- phase 2: sub-warp per point
-      if (nv > 0) wait_rows();
-      for (int k = sg; k < kfit; k += RPI) {
-        const int s0 = (int)sm.ri[k], n = (int)sm.go[k];
-        float acc[VEC];
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
-#pragma unroll 4
-        for (int j = 0; j < n; ++j) {
-          float fx[VEC];
-          unpack16<T, VEC>(*reinterpret_cast<const uint4*>(rows_s + (size_t)(s0 + j) * RS + lir * 16), fx);
-          const float e = sm.wt[s0 + j][gk];
-#pragma unroll
-          for (int q = 0; q < VEC; ++q) acc[q] = fmaf(e, fx[q], acc[q]);
-        }
-        const float scale = sm.dq[k][gk];
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) acc[q] *= scale;
-        stg_stream16(ob + (pg + k) * (int64_t)row_bytes, pack16<T, VEC>(acc));    // unseen point: exact zeros
-      }
-      pg += kfit;
-    }
-  }
-}
-
-template <typename T> static bool lane_fwd_ok(const VAParams& P) {
-  constexpr int V16 = Vec16<T>::N;
-  const int C = P.C;
-  if (P.G != 4 || C % V16 != 0 || C / V16 > 32 || C / V16 < 4) return false;
-  const int cv = C / V16;
-  if ((cv & (cv - 1)) != 0) return false;
-  if (!aligned16(P.x) || !aligned16(P.out) || !aligned16(P.compat)) return false;
-  if (P.att != nullptr && !aligned16(P.att)) return false;
-  if (P.seg_max != nullptr && (!aligned16(P.seg_max) || !aligned16(P.seg_den) || !aligned16(P.seg_arg))) return false;
-  if (P.V >= (1ll << 31) || P.R >= (1ll << 32)) return false;
-  return true;
-}
-
-bool va_lane_fwd_applicable(const VAParams& P, int dtype) {
-  switch (dtype) {
-    case DVA_F32: return lane_fwd_ok<float>(P);
-    case DVA_BF16: return lane_fwd_ok<__nv_bfloat16>(P);
-    case DVA_F16: return lane_fwd_ok<__half>(P);
-    default: return false;
-  }
-}
-
-template <typename T, int LPR>
-static int lane_fwd_launch(const VAParams& P, cudaStream_t st) {
-  auto kern = va_lane_fwd_kernel<T, LPR>;
-  const size_t smem = (size_t)kLaneWarps * 32 * LPR * 16;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return fail((int)e, "va_lane_fwd: cannot reserve shared memory");
-  int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kLaneWarps * 32, smem) != cudaSuccess || occ < 1) occ = 1;
-  int64_t grid = (int64_t)kNumSMs * occ;
-  const int64_t warps = grid * kLaneWarps;
-  int64_t pr = (P.N + warps * 4 - 1) / (warps * 4);
-  if (pr < 8) pr = 8;
-  const int64_t n_ranges = (P.N + pr - 1) / pr;
-  const int64_t need = (n_ranges + kLaneWarps - 1) / kLaneWarps;
-  if (grid > need) grid = need;
-  if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, kLaneWarps * 32, smem, st>>>(P, (int)pr);
-  return check_launch("va_lane_fwd");
-}
-
-template <typename T>
-static int lane_fwd_typed(const VAParams& P, cudaStream_t st) {
-  switch (P.C / Vec16<T>::N) {
-    case 4: return lane_fwd_launch<T, 4>(P, st);
-    case 8: return lane_fwd_launch<T, 8>(P, st);
-    case 16: return lane_fwd_launch<T, 16>(P, st);
-    default: return lane_fwd_launch<T, 32>(P, st);
-  }
-}
-
-int va_lane_fwd(const VAParams& P, int dtype, cudaStream_t st) {
-  switch (dtype) {
-    case DVA_F32: return lane_fwd_typed<float>(P, st);
-    case DVA_BF16: return lane_fwd_typed<__nv_bfloat16>(P, st);
-    default: return lane_fwd_typed<__half>(P, st);
   }
 }
 

@@ -200,7 +200,7 @@ def main():
         emit("csr_select_values", "C1", T(lambda: csrmod.select_values(p, sel)), units=sel.numel(),
              unit_name="mgroups_per_s", note="new pointers + value index for a random half of the groups")
 
-    # ---- L1 / I1 / I4 mapping re-indexing on the device (torch sort + our CSR kernels) ----------
+    # ---- I1 / I4 mapping re-indexing on the device (native counting sort + warp rank sort, csrc/mapping_build.cu) ----
     if want("mapping"):
         from deepviewagg_b200.core.multimodal.image import ImageMapping
         npts, nimg = 400_000, 64
@@ -217,6 +217,7 @@ def main():
         emit("image_mapping_from_dense", "I1", T(build), units=m, unit_name="mtriples_per_s",
              note=f"{m} (point,image,pixel) triples, {npts} points, {nimg} images")
         vox = torch.randint(0, npts // 4, (npts,), device=dev, generator=gen)
+        vox[: npts // 4] = torch.arange(npts // 4, device=dev)          # every output voxel present (image.py:2220)
         emit("select_points_merge", "I4", T(lambda: mp.select_points(vox, mode="merge")), units=m,
              unit_name="mtriples_per_s", note="4:1 voxel merge (strided sparse conv re-indexing)")
 
