@@ -26,6 +26,7 @@ cpu_baseline / --impl reference : the oracle port of the reference's PyTorch pat
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -80,6 +81,8 @@ def parse():
     p.add_argument("--rounds", type=int, default=0, help="timed repetitions of the K-step region (0 = from a 2.5 s budget)")
     p.add_argument("--sweep", default="", help="comma list of views per point (BASELINE config #5: 8,16,32,64): extra "
                                                "device-resident measurements under roofline_detail.sweep")
+    p.add_argument("--no-variant-b", action="store_true", help="skip the variant-B side measurement (QKVBimodalCSRPool: scores "
+                                                              "from K [V,G*D] and Q [N,G*D]; roofline_detail.variant_b)")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-modules", action="store_true", help="skip the whole-module side measurements (roofline_detail.modules)")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -508,6 +511,11 @@ def main():
 
     if rank == 0 and world == 1 and args.sweep:
         extra_roof["sweep"] = run_sweep(args, dev, peak, [int(t) for t in args.sweep.split(",") if t])
+    if rank == 0 and world == 1 and not args.no_variant_b:
+        try:
+            extra_roof["variant_b"] = run_variant_b(args, plan, dev, peak, N, V)
+        except Exception as e:
+            extra_roof["variant_b"] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0 and world == 1 and not args.no_modules:
         try:
             extra_roof["modules"] = run_module_workloads(dev, peak)
@@ -636,6 +644,51 @@ def run_sweep(args, dev, peak, views_list, steps=10, warmup=3):
         del plan
         torch.cuda.empty_cache()
     return out
+
+
+def run_variant_b(args, plan, dev, peak, N, V, D=8, steps=10, warmup=3):
+    """Variant B of SURVEY 8(d) (QKVBimodalCSRPool, pooling.py:499-530) on the headline shape: the scores are not
+    given but computed from keys K [V, G*D] (one row per view) and queries Q [N, G*D] (one row per point, never
+    expanded to the views); the backward also emits dK and dQ.  Two launches each way (dva_qk_scores_* then the fused
+    attention pair, compat [V,G] = 16 B per view in between).  Bytes: variant A + (V + N) G D 4 (read K, Q) forward,
+    + the same again backward (write dK, dQ), as SURVEY 8(d) counts them -- the 16 B per view of compat traffic the
+    two-launch pipeline adds is NOT credited."""
+    from deepviewagg_b200 import _lib
+    lib = _lib.load()
+    G, C = args.groups, args.channels
+    s = 4 if args.dtype == "f32" else 2
+    gen = torch.Generator(device=dev).manual_seed(4242)
+    K = torch.randn(V, G * D, device=dev, generator=gen)
+    Q = torch.randn(N, G * D, device=dev, generator=gen)
+    dK, dQ = torch.empty_like(K), torch.empty_like(Q)
+    scale = 1.0 / math.sqrt(D)
+    st = torch.cuda.current_stream(dev).cuda_stream
+
+    def fwd():
+        _lib.check(lib.dva_qk_scores_fwd(K.data_ptr(), Q.data_ptr(), plan.ptr.data_ptr(), plan.compat.data_ptr(),
+                                         N, V, G, D, scale, st), "dva_qk_scores_fwd")
+        plan.forward_device()
+
+    def bwd():
+        plan.backward_device()
+        _lib.check(lib.dva_qk_scores_bwd(K.data_ptr(), Q.data_ptr(), plan.ptr.data_ptr(), plan.gcompat.data_ptr(),
+                                         dK.data_ptr(), dQ.data_ptr(), N, V, G, D, scale, st), "dva_qk_scores_bwd")
+    fw, bw = [], []
+    for i in range(warmup + steps):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record(); fwd(); e[1].record(); bwd(); e[2].record()
+        torch.cuda.synchronize()
+        if i >= warmup:
+            fw.append(e[0].elapsed_time(e[1])); bw.append(e[1].elapsed_time(e[2]))
+    f_ms, b_ms = statistics.median(fw), statistics.median(bw)
+    bf, bb = algorithmic_bytes(N, V, C, G, s)
+    qk = (V + N) * G * D * 4
+    bf, bb = bf + qk, bb + qk
+    return {"what": "qk_scores + fused attention, fwd + bwd incl. dK, dQ (QKVBimodalCSRPool, nc_qk = %d, dim_scaling)" % D,
+            "fwd_ms": f_ms, "bwd_ms": b_ms, "mpoints_per_s": N / (f_ms + b_ms) / 1e3,
+            "algorithmic_bytes": bf + bb, "fwd_frac": bf / (f_ms * 1e-3) / 1e9 / peak,
+            "bwd_frac": bb / (b_ms * 1e-3) / 1e9 / peak, "step_frac": (bf + bb) / ((f_ms + b_ms) * 1e-3) / 1e9 / peak,
+            "launches_per_step": 4}
 
 
 def run_e2e(args, plan, dist, dev, world, N, V, n_bucket):

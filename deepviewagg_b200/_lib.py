@@ -72,6 +72,9 @@ SIGNATURES = {
                               _vp, _sz, _vp]),
     "dva_bn_act_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _i32, _i32, _vp, _sz,
                               _vp]),
+    "dva_mlp_layer_bwd_supported": (_i32, [_i64, _i64, _i64]),
+    "dva_mlp_layer_bwd_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "dva_mlp_layer_bwd": (_i32, [_vp] * 11 + [_i64, _i64, _i64, _f32, _vp, _sz, _vp]),
     "dva_zbuffer_splat": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64,
                                  _i32, _vp]),
     "dva_splat_boxes": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _f64, _f64, _f64,

@@ -346,7 +346,8 @@ extern "C" int dva_bn_act_bwd(const void* dy, const void* z, const float* gamma,
     if (dgamma_dbeta) cudaMemsetAsync(dgamma_dbeta, 0, 2 * C * sizeof(float), st);
     return DVA_OK;
   }
-  if (!dy || !z || !mean || !invstd || !dz || !dgamma_dbeta) return fail(DVA_EINVAL, "bn_act_bwd: null pointer");
+  // dz == nullptr: statistics pass only (the caller differentiates the rows itself: mlp_layer.cu)
+  if (!dy || !z || !mean || !invstd || !dgamma_dbeta) return fail(DVA_EINVAL, "bn_act_bwd: null pointer");
   if (!workspace || workspace_bytes < dva_bn_workspace_bytes(R, C)) return fail(DVA_EINVAL, "bn_act_bwd: workspace too small");
   BN_TYPED(dtype, {
     const int v1 = pick_vec<T>(C, z, dy), v2 = pick_vec<T>(C, dz, nullptr);
@@ -368,6 +369,7 @@ extern "C" int dva_bn_act_bwd(const void* dy, const void* z, const float* gamma,
     // dgamma_dbeta = [sum g ; sum g*zhat]  (note the order: [0] = d beta, [1] = d gamma)
     bn_bwd_finalize_kernel<<<(int)((2 * C + 7) / 8), 256, 0, st>>>((const float*)workspace, grid, (int)C, dgamma_dbeta);
     if ((rc = check_launch("bn_bwd_finalize"))) return rc;
+    if (!dz) return DVA_OK;
     if (vec > 1)
       bn_bwd_apply_kernel<T, Vec16<T>::N><<<bn_grid_stream(R, (int)C, Vec16<T>::N), kBnThreads, 0, st>>>(
           (const T*)dy, (const T*)z, mean, invstd, gamma, beta, dgamma_dbeta, (T*)dz, R, (int)C, slope, training);

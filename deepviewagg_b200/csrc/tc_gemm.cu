@@ -42,6 +42,7 @@ constexpr int kStages = 3;                 // stages of the streamed-weight rows
 constexpr int kStagesT = 6;                // stages of the rows kernel with the weight in tensor memory
 constexpr int kThreads = 320;
 constexpr int kSplitThreads = 128;
+constexpr int kThreadsAll = kThreads + kSplitThreads;   // + a second set of split warps (warps 10-13)
 constexpr uint32_t kTmemCols = 256;        // two 128-column accumulators
 constexpr uint32_t kTmemColsW = 512;       // + weight hi at column 256, weight lo at column 384 (K <= 128 each)
 
@@ -178,7 +179,7 @@ struct RowsParams {
 //                rate would otherwise eat the whole 128 B/clk of shared-memory bandwidth by itself;
 // WTMEM = false: wider layers: weight k-blocks are streamed through shared memory next to X (3 x 64 KB).
 template <bool WTMEM>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsAll, 1)
 tc_rows_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
                const __grid_constant__ CUtensorMap map_wlo, const RowsParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -280,12 +281,19 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         if (++acc == 2) { acc = 0; aph ^= 1u; }
       }
     }
-  } else if (warp < 2 + kSplitThreads / 32) {
+  } else if (warp < 2 + kSplitThreads / 32 || warp >= kThreads / 32) {
     // ===================== split warps: X -> (hi in place, lo next to it) =====================
-    const int tid = threadIdx.x - 64;
-    int s = 0; uint32_t ph = 0;
+    // two sets of four warps (2-5 and 10-13) take the k-blocks alternately: the chain wait -> LDS -> split ->
+    // STS -> proxy fence -> arrive of one block overlaps the next block's
+    const int set = warp >= kThreads / 32 ? 1 : 0;
+    const int tid = threadIdx.x - (set ? kThreads : 64);
+    int s = 0; uint32_t ph = 0, cnt = 0;
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-      for (int kb = 0; kb < KB; ++kb) {
+      for (int kb = 0; kb < KB; ++kb, ++cnt) {
+        if ((int)(cnt & 1u) != set) {
+          if (++s == NS) { s = 0; ph ^= 1u; }
+          continue;
+        }
         mbar_wait(full_tma(s), ph);
         float4* hi = reinterpret_cast<float4*>(st_base + (size_t)s * kStageBytes);
         float4* lo = reinterpret_cast<float4*>(st_base + (size_t)s * kStageBytes + kTileBytes);
@@ -406,9 +414,10 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 // partial tile; dw_reduce_kernel adds the slices in a fixed order (deterministic, no atomics).
 constexpr int kDwRows = 32;                      // contraction rows per stage
 constexpr int kGroupBytes = kDwRows * 128;       // one [32 x 32] box
-constexpr int kDwOperandBytes = 4 * kGroupBytes; // 4 column groups = 128 columns: 16 KB
-constexpr int kDwStages = 4;
+constexpr int kDwMaxStages = 6;                  // tensor memory: 128 accumulator columns + 64 per stage <= 512
+constexpr size_t kDwSmemBudget = 200 * 1024;
 constexpr uint32_t kDwTmemCols = 512;            // accumulator [0,128) + per stage dZ_hi | dZ_lo (32 + 32 columns)
+constexpr int kDwThreads = kThreadsAll;            // the second set of split warps (10-13) takes the odd row blocks
 
 __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr) {
   return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)(kGroupBytes >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
@@ -421,6 +430,8 @@ struct DwParams {
   float* partial;        // [splits, n_pad, k_pad]
   int64_t V, blocks_total, blocks_per_split;
   int n_out, k_in, n_pad, k_pad, k_tiles, splits;
+  int stages;            // 4 .. kDwMaxStages: as many as shared memory (compact stages) and tensor memory (64 columns each) hold
+  uint32_t a_bytes, b_bytes;   // per stage: dZ boxes (4 KB per 32 output rows), X boxes (4 KB per 32 columns; hi and lo each)
 };
 
 // The dZ operand never goes back to shared memory: split warp g (TMEM lane quadrant g = output rows 32 g ..)
@@ -429,13 +440,16 @@ struct DwParams {
 // tcgen05.st each -- lane = output row, 32 columns = the 32 contraction rows of the stage.  The tensor core
 // then reads A from TMEM and only X from shared memory: 144 KB instead of 224 KB of shared-memory traffic
 // per 32 KB of HBM traffic (the all-shared-memory version was bound by the 128 B/clk of shared memory).
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kDwThreads, 1)
 tc_dw_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__ CUtensorMap map_x, const DwParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr int NS = kDwStages;
-  constexpr uint32_t kStageBytes = 3u * kDwOperandBytes;      // dZ (raw), X_hi, X_lo
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * kStageBytes);
+  // The per-stage chain TMA -> split -> MMA -> empty is ~3 us long whatever the width, so the stage count sets the
+  // pace (0.84 us per 32 rows with 4): narrow layers pack their stages (only the boxes they use) and get up to 6.
+  const int NS = p.stages;
+  const uint32_t kStageBytes = p.a_bytes + 2u * p.b_bytes;    // dZ (raw), X_hi, X_lo
+  const uint32_t x_hi_off = p.a_bytes, x_lo_off = p.a_bytes + p.b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NS * kStageBytes);
   const uint32_t bar0 = smem_u32(bars);
   auto full_tma = [&](int s) { return bar0 + 8u * s; };
   auto full_cvt = [&](int s) { return bar0 + 8u * (NS + s); };
@@ -476,7 +490,7 @@ tc_dw_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__
         for (int g = 0; g < a_groups; ++g)
           tma_load_2d(smem_u32(st + g * kGroupBytes), &map_dz, nt * kTile + g * 32, row, full_tma(s));
         for (int g = 0; g < b_groups; ++g)
-          tma_load_2d(smem_u32(st + kDwOperandBytes + g * kGroupBytes), &map_x, kt * kTile + g * 32, row, full_tma(s));
+          tma_load_2d(smem_u32(st + x_hi_off + g * kGroupBytes), &map_x, kt * kTile + g * 32, row, full_tma(s));
         if (++s == NS) { s = 0; ph ^= 1u; }
       }
     }
@@ -489,25 +503,35 @@ tc_dw_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__
         tc_fence_after();
         uint8_t* st = smem + (size_t)s * kStageBytes;
         const uint32_t a_hi = tmem_base + 128u + (uint32_t)s * 64u, a_lo = a_hi + 32u;
-        const uint64_t x_hi = smem_desc_mn_sw128(smem_u32(st + kDwOperandBytes));
-        const uint64_t x_lo = smem_desc_mn_sw128(smem_u32(st + 2 * kDwOperandBytes));
+        const uint64_t x_hi = smem_desc_mn_sw128(smem_u32(st + x_hi_off));
+        const uint64_t x_lo = smem_desc_mn_sw128(smem_u32(st + x_lo_off));
+        // UMMA N = the X columns this tile really has (32 per box): packed stages hold no more than that
+        const uint32_t idesc = (kIdescTf32TsMN & ~(0x3fu << 17)) | ((uint32_t)(b_groups * 32 >> 3) << 17);
 #pragma unroll
         for (int k = 0; k < kDwRows / 8; ++k) {          // 8 contraction rows: 8 TMEM columns of dZ^T, two 512-byte atoms of X
           const uint64_t o = (uint64_t)(k * (1024 >> 4));
-          umma_tf32_ts(tmem_base, a_lo + 8u * k, x_hi + o, kIdescTf32TsMN, (uint32_t)((b | k) != 0));
-          umma_tf32_ts(tmem_base, a_hi + 8u * k, x_lo + o, kIdescTf32TsMN, 1u);
-          umma_tf32_ts(tmem_base, a_hi + 8u * k, x_hi + o, kIdescTf32TsMN, 1u);
+          umma_tf32_ts(tmem_base, a_lo + 8u * k, x_hi + o, idesc, (uint32_t)((b | k) != 0));
+          umma_tf32_ts(tmem_base, a_hi + 8u * k, x_lo + o, idesc, 1u);
+          umma_tf32_ts(tmem_base, a_hi + 8u * k, x_hi + o, idesc, 1u);
         }
         umma_commit(empty(s));
         if (b == nblk - 1) umma_commit(tmem_full);
         if (++s == NS) { s = 0; ph ^= 1u; }
       }
     }
-  } else if (warp < 2 + kSplitThreads / 32) {
-    const int tid = threadIdx.x - 64;
+  } else if (warp < 2 + kSplitThreads / 32 || warp >= kThreads / 32) {
+    // Two sets of four split warps take the row blocks alternately (set 0 = warps 2-5: even blocks, set 1 = warps
+    // 10-13: odd ones): the chain wait -> 32 LDS -> split -> tcgen05.st -> wait::st -> X split -> fence -> arrive
+    // of one block overlaps the next block's (8 M x 128 x 128: 1.77 -> 1.54 ms).
+    const int set = warp >= kThreads / 32 ? 1 : 0;
+    const int tid = threadIdx.x - (set ? kThreads : 64);
     const int g = warp & 3;                              // TMEM lane quadrant = dZ column group of this warp
     int s = 0; uint32_t ph = 0;
     for (int64_t b = 0; b < nblk; ++b) {
+      if ((int)(b & 1) != set) {
+        if (++s == NS) { s = 0; ph ^= 1u; }
+        continue;
+      }
       mbar_wait(full_tma(s), ph);
       uint8_t* st = smem + (size_t)s * kStageBytes;
       if (g < a_groups) {
@@ -528,8 +552,8 @@ tc_dw_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__
         tmem_st_wait();
       }
       {
-        float4* hi = reinterpret_cast<float4*>(st + kDwOperandBytes);
-        float4* lo = reinterpret_cast<float4*>(st + 2 * kDwOperandBytes);
+        float4* hi = reinterpret_cast<float4*>(st + x_hi_off);
+        float4* lo = reinterpret_cast<float4*>(st + x_lo_off);
         for (int i = 0; i < b_groups * (kGroupBytes / 16) / kSplitThreads; ++i) {
           const int e = i * kSplitThreads + tid;
           const float4 v = hi[e];
@@ -717,11 +741,11 @@ extern "C" int dva_tc_rows_gemm(const float* X, const float* W, float* D, int64_
   if (resident) {
     e = cudaFuncSetAttribute(tc::tc_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "tc_rows_gemm: cannot reserve shared memory");
-    tc::tc_rows_kernel<true><<<grid, tc::kThreads, smem, st>>>(mx, mh, ml, p);
+    tc::tc_rows_kernel<true><<<grid, tc::kThreadsAll, smem, st>>>(mx, mh, ml, p);
   } else {
     e = cudaFuncSetAttribute(tc::tc_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "tc_rows_gemm: cannot reserve shared memory");
-    tc::tc_rows_kernel<false><<<grid, tc::kThreads, smem, st>>>(mx, mh, ml, p);
+    tc::tc_rows_kernel<false><<<grid, tc::kThreadsAll, smem, st>>>(mx, mh, ml, p);
   }
   return check_launch("tc_rows_gemm");
 }
@@ -773,10 +797,15 @@ extern "C" int dva_tc_dw_gemm(const float* dZ, const float* X, float* D, int64_t
   if (rc) return rc;
   rc = tc::make_map(&mx, X, V, k_in, ldx, tc::kDwRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (rc) return rc;
-  const size_t smem = 1024 + (size_t)tc::kDwStages * 3 * tc::kDwOperandBytes + 256;
+  const int ag = (int)(n_out >= tc::kTile ? 4 : (n_out + 31) / 32), bg = (int)(k_in >= tc::kTile ? 4 : (k_in + 31) / 32);
+  p.a_bytes = (uint32_t)ag * tc::kGroupBytes; p.b_bytes = (uint32_t)bg * tc::kGroupBytes;
+  const size_t stage_bytes = p.a_bytes + 2 * (size_t)p.b_bytes;
+  p.stages = (int)(tc::kDwSmemBudget / stage_bytes);
+  if (p.stages > tc::kDwMaxStages) p.stages = tc::kDwMaxStages;
+  const size_t smem = 1024 + (size_t)p.stages * stage_bytes + 256;
   cudaError_t e = cudaFuncSetAttribute(tc::tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail((int)e, "tc_dw_gemm: cannot reserve shared memory");
-  tc::tc_dw_kernel<<<nt * kt * sp, tc::kThreads, smem, st>>>(mz, mx, p);
+  tc::tc_dw_kernel<<<nt * kt * sp, tc::kDwThreads, smem, st>>>(mz, mx, p);
   rc = check_launch("tc_dw_gemm");
   if (rc) return rc;
   const int64_t total = n_out * k_in;

@@ -757,6 +757,83 @@ class _LinearStats(torch.autograd.Function):
         return gx, gw, None, None, None, None
 
 
+class _MLPLayer(torch.autograd.Function):
+    """One narrow MLP layer act(BatchNorm1d(x @ weight.T)) in training mode (base_modules.py:38-48) as ONE autograd
+    node: forward = GEMM with the batch statistics in its epilogue (dva_linear_bnstats_fwd) + the apply pass;
+    backward = the statistics pass + ONE kernel for dz (kept on chip), dX and dW (dva_mlp_layer_bwd)."""
+
+    @staticmethod
+    @_fwd_f32
+    def forward(ctx, x, weight, gamma, beta, running_mean, running_var, momentum, eps, slope):
+        require_cuda(x, weight, gamma, beta)
+        lib = _lib.load()
+        x, w = x.float().contiguous(), weight.float().contiguous()
+        M, K = x.shape
+        N = w.shape[0]
+        dev = x.device
+        z = torch.empty((M, N), dtype=torch.float32, device=dev)
+        mean = torch.empty(N, dtype=torch.float32, device=dev)
+        invstd = torch.empty(N, dtype=torch.float32, device=dev)
+        g = gamma.detach().float().contiguous() if gamma is not None else None
+        b = beta.detach().float().contiguous() if beta is not None else None
+        stage = []
+        rm, rv = running_mean, running_var
+        for name, buf in (("m", rm), ("v", rv)):
+            if buf is not None and (buf.dtype != torch.float32 or not buf.is_contiguous()):
+                stage.append((name, buf, buf.float().contiguous()))
+        for name, _, tmp in stage:
+            if name == "m":
+                rm = tmp
+            else:
+                rv = tmp
+        ws_bytes = max(int(lib.dva_linear_bnstats_workspace_bytes(N, K)), int(lib.dva_bn_workspace_bytes(M, N)))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        y = torch.empty_like(z)
+        with torch.cuda.device(dev):
+            check(lib.dva_linear_bnstats_fwd(ptr(x), ptr(w), ptr(z), M, N, K, float(eps), float(momentum), ptr(mean),
+                                             ptr(invstd), ptr(rm), ptr(rv), ptr(ws), ws_bytes, stream_ptr()),
+                  "dva_linear_bnstats_fwd")
+            # apply half: eval-style call on the batch statistics (the kernel only reads mean / invstd)
+            check(lib.dva_bn_act_fwd(ptr(z), ptr(g), ptr(b), ptr(mean), ptr(mean), ptr(mean), ptr(invstd), ptr(y),
+                                     M, N, float(eps), 0.0, float(slope), 0, dtype_code(z), ptr(ws), ws_bytes,
+                                     stream_ptr()), "dva_bn_act_fwd")
+        for _, buf, tmp in stage:
+            buf.copy_(tmp)
+        ctx.cfg = (float(slope), gamma is not None, beta is not None,
+                   gamma.dtype if gamma is not None else (beta.dtype if beta is not None else None), weight.dtype)
+        ctx.save_for_backward(x, w, z, g, b, mean, invstd)
+        return y
+
+    @staticmethod
+    @_bwd
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        x, w, z, g, b, mean, invstd = ctx.saved_tensors
+        slope, has_g, has_b, pdt, wdt = ctx.cfg
+        lib = _lib.load()
+        M, K = x.shape
+        N = w.shape[0]
+        dy = dy.float().contiguous()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w)
+        sums = torch.empty((2, N), dtype=torch.float32, device=x.device)
+        ws_bytes = int(lib.dva_mlp_layer_bwd_workspace_bytes(M, N, K))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.dva_mlp_layer_bwd(ptr(dy), ptr(z), ptr(x), ptr(w), ptr(g), ptr(b), ptr(mean), ptr(invstd),
+                                        ptr(dx), ptr(dw), ptr(sums), M, N, K, slope, ptr(ws), ws_bytes, stream_ptr()),
+                  "dva_mlp_layer_bwd")
+        gw = sums[1].to(pdt) if has_g else None
+        gb = sums[0].to(pdt) if has_b else None
+        return dx, (dw.to(wdt) if ctx.needs_input_grad[1] else None), gw, gb, None, None, None, None, None
+
+
+# The fused backward runs on the legacy mma.sync pipe, which it saturates (5 clocks per m16n8k8 per SM): 137 us at
+# 1.28 M x 32 x 32 against 260 - 340 us for the three kernels it replaces, but no faster than them at K = 64
+# (329 against 294 us), where dX rides the tcgen05 kernel -> layers with K <= 32 only.
+_MLP_LAYER_FUSED = {"on": os.environ.get("DVA_MLP_LAYER_FUSED", "1") != "0", "max_k": 32}
+
+
 def linear_bn_act(x, weight, bn, negative_slope=1.0):
     """act(BatchNorm1d(x @ weight.T)): one MLP layer of the pools (base_modules.py:38-48).  In training,
     when the layer is wide enough for the tcgen05 kernel and has at most 128 output channels, the batch
@@ -775,6 +852,10 @@ def linear_bn_act(x, weight, bn, negative_slope=1.0):
             momentum = 1.0 / float(bn.num_batches_tracked)
     rm = bn.running_mean if bn.track_running_stats else None
     rv = bn.running_var if bn.track_running_stats else None
+    if (_MLP_LAYER_FUSED["on"] and K <= _MLP_LAYER_FUSED["max_k"] and lib.dva_mlp_layer_bwd_supported(M, N, K)
+            and torch.is_grad_enabled()
+            and (x.requires_grad or weight.requires_grad)):
+        return _MLPLayer.apply(x, weight, bn.weight, bn.bias, rm, rv, momentum, bn.eps, negative_slope)
     z, mean, invstd = _LinearStats.apply(x, weight, rm, rv, momentum, bn.eps)
     return _BNAct.apply(z, bn.weight, bn.bias, rm, rv, True, momentum, bn.eps, negative_slope, mean, invstd)
 

@@ -243,8 +243,9 @@ int dva_linear_gemm(const float* A, const float* B, float* D, int64_t M, int64_t
  *   shifted sum / sum of squares while storing; a one-warp-per-column kernel combines the per-CTA
  *   partials in fp64 (fixed order) into mean / invstd [n_out] (biased variance) and updates the running
  *   buffers (momentum, unbiased variance) like nn.BatchNorm1d.  The apply half is dva_bn_act_fwd with
- *   training = 0 on these mean / invstd.  supported(): 32 < n_out <= 128, n_out % 4 == 0, k_red > 32,
- *   k_red % 4 == 0 (the shapes dva_linear_gemm serves with the tcgen05 rows kernel); else DVA_EUNSUPPORTED.
+ *   training = 0 on these mean / invstd.  supported(): 32 <= n_out <= 128, n_out % 4 == 0, k_red >= 8,
+ *   k_red % 4 == 0 (the shapes dva_linear_gemm serves with the tcgen05 rows kernel; with DVA_TC_NARROW=0 in the
+ *   environment only n_out > 32 and k_red > 32, the round-1 routing); else DVA_EUNSUPPORTED.
  * ------------------------------------------------------------------------------------------ */
 int dva_linear_bnstats_supported(int64_t M, int64_t n_out, int64_t k_red);
 size_t dva_linear_bnstats_workspace_bytes(int64_t n_out, int64_t k_red);
@@ -260,7 +261,7 @@ int dva_linear_bnstats_fwd(const float* X, const float* W, float* D, int64_t M, 
  *   momentum update), y = act(gamma * (z - mean) * invstd + beta), act(a) = a > 0 ? a : slope * a
  *   (slope = 1: plain BatchNorm).  z, y [R,C] (dtype); gamma/beta nullable; mean/invstd [C] fp32 are
  *   written in training and READ in eval (host passes running_mean and rsqrt(running_var + eps)).
- *   Backward: dz [R,C]; dbeta_dgamma [2,C] fp32 = (sum g ; sum g * zhat) with g = dy * act'.
+ *   Backward: dz [R,C] (NULL: statistics pass only); dbeta_dgamma [2,C] fp32 = (sum g ; sum g * zhat) with g = dy * act'.
  *   workspace: dva_bn_workspace_bytes(R, C) bytes (per-CTA partial sums, deterministic).
  * ------------------------------------------------------------------------------------------ */
 size_t dva_bn_workspace_bytes(int64_t R, int64_t C);
@@ -272,6 +273,25 @@ int dva_bn_act_bwd(const void* dy, const void* z, const float* gamma, const floa
                    const float* mean, const float* invstd, void* dz, float* dbeta_dgamma, int64_t R,
                    int64_t C, float slope, int training, int dtype, void* workspace,
                    size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * P9 / P5  backward of one narrow MLP layer  a = LeakyReLU(BatchNorm1d(x . W^T))   (training statistics)
+ *   replaces the autograd chain of base_modules.py:38-48 for the layers of the map encoders
+ *   (DeepSetFeat / MLPSetFeat, pooling.py:645-656, 686: 8 / 32 / 64 -> 32 on one row per view):
+ *   pass 1 = the statistics half of dva_bn_act_bwd (dz = NULL there: reduction only), pass 2 = ONE kernel that
+ *   forms dz = gamma invstd (g - mean(g) - zhat mean(g zhat)) on chip and emits dX = dz . W and dW = dz^T . x
+ *   from the same tile (3xTF32 mma.sync, fp32-grade): 3 reads + 1 write of the rows instead of 5 + 2.
+ *   dA, Z [M,N] fp32 (gradient of the layer output, saved pre-BatchNorm linear output); X [M,K] fp32 layer input;
+ *   W [N,K]; gamma / beta nullable; mean / invstd [N] of the forward; dX [M,K] nullable (first layer);
+ *   dW [N,K]; dbeta_dgamma [2,N] = (sum g ; sum g zhat).  supported(): N <= 32, K <= 64, both % 4 == 0.
+ *   Row pointers 16-byte aligned.  Deterministic (per-CTA partials summed in a fixed order).
+ * ------------------------------------------------------------------------------------------ */
+int dva_mlp_layer_bwd_supported(int64_t M, int64_t N, int64_t K);
+size_t dva_mlp_layer_bwd_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int dva_mlp_layer_bwd(const float* dA, const float* Z, const float* X, const float* W, const float* gamma,
+                      const float* beta, const float* mean, const float* invstd, float* dX, float* dW,
+                      float* dbeta_dgamma, int64_t M, int64_t N, int64_t K, float slope, void* workspace,
+                      size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Z3  z-buffer visibility from splatting    replaces visibility.py:1073-1195 (CPU/numba oracle)

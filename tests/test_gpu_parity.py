@@ -524,3 +524,72 @@ def test_tc_linear_vs_fp64(M, K, N):
     x2 = torch.randn(100, 130, generator=gen).cuda()
     w2 = torch.randn(66, 130, generator=gen).cuda()
     close(ops.linear(x2, w2).double(), x2.double() @ w2.double().t(), 3e-6, "padded widths")
+
+
+# ------------------------------------------------------------------------------------------------
+# one narrow MLP layer as a single autograd node (fused backward: dz on chip, dX and dW from one tile) vs fp64 torch
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,K,N,need_dx", [(5000, 32, 32, True), (70001, 8, 32, False), (30000, 64, 32, True),
+                                           (777, 12, 16, True), (33, 32, 32, True), (100000, 32, 32, True),
+                                           (15, 64, 32, True), (4099, 16, 32, False), (2000, 32, 8, True)])
+def test_mlp_layer_fused_backward_vs_fp64(M, K, N, need_dx):
+    from deepviewagg_b200 import ops, _lib
+    assert _lib.load().dva_mlp_layer_bwd_supported(M, N, K)
+    gen = torch.Generator().manual_seed(M + K + N)
+    x0 = torch.randn(M, K, generator=gen) * 1.5 + 0.3
+    w0 = torch.randn(N, K, generator=gen) / math.sqrt(K)
+    g = torch.randn(M, N, generator=gen).cuda()
+    bn_a = torch.nn.BatchNorm1d(N, momentum=0.1).double().cuda()
+    bn_b = torch.nn.BatchNorm1d(N, momentum=0.1).cuda()
+    with torch.no_grad():
+        bn_b.weight.copy_(torch.rand(N, generator=gen) + 0.5)
+        bn_b.bias.copy_(torch.randn(N, generator=gen) * 0.3)
+        bn_a.weight.copy_(bn_b.weight.double()), bn_a.bias.copy_(bn_b.bias.double())
+    xa = x0.double().cuda().requires_grad_(need_dx)
+    wa = w0.double().cuda().requires_grad_(True)
+    xb = x0.cuda().requires_grad_(need_dx)
+    wb = w0.cuda().requires_grad_(True)
+    ya = torch.nn.functional.leaky_relu(bn_a(xa @ wa.t()), 0.2)
+    if not _lib.load().dva_linear_bnstats_supported(M, N, K):
+        pytest.skip("the forward of this shape takes the unfused route")
+    old_max_k = ops._MLP_LAYER_FUSED["max_k"]
+    ops._MLP_LAYER_FUSED["max_k"] = 64            # the routing prefers the unfused chain above K = 32; test the kernel anyway
+    try:
+        yb = ops.linear_bn_act(xb, wb, bn_b, negative_slope=0.2)
+    finally:
+        ops._MLP_LAYER_FUSED["max_k"] = old_max_k
+    assert type(yb.grad_fn).__name__.startswith("_MLPLayer"), type(yb.grad_fn).__name__
+    # the unfused chain on the same inputs: same forward kernels, hence the same LeakyReLU slope decisions
+    bn_c = torch.nn.BatchNorm1d(N, momentum=0.1).cuda()
+    bn_c.load_state_dict({k: v.float() for k, v in bn_a.state_dict().items()})
+    with torch.no_grad():
+        bn_c.running_mean.zero_(), bn_c.running_var.fill_(1.0), bn_c.num_batches_tracked.zero_()
+    xc = x0.cuda().requires_grad_(need_dx)
+    wc = w0.cuda().requires_grad_(True)
+    ops._MLP_LAYER_FUSED["on"] = False
+    try:
+        yc = ops.linear_bn_act(xc, wc, bn_c, negative_slope=0.2)
+    finally:
+        ops._MLP_LAYER_FUSED["on"] = True
+    gc = torch.autograd.grad((yc * g).sum(), ([xc] if need_dx else []) + [wc, bn_c.weight, bn_c.bias])
+    ins_a = ([xa] if need_dx else []) + [wa, bn_a.weight, bn_a.bias]
+    ins_b = ([xb] if need_dx else []) + [wb, bn_b.weight, bn_b.bias]
+    ga = torch.autograd.grad((ya * g.double()).sum(), ins_a)
+    gb = torch.autograd.grad((yb * g).sum(), ins_b)
+    close(yb, ya, 2e-5, "mlp layer y")
+    names = (["dx"] if need_dx else []) + ["dw", "dgamma", "dbeta"]
+    assert torch.equal(yb, yc)
+    for n, a, c, b in zip(names, gb, gc, ga):
+        scale = max(1.0, float(b.abs().max()))
+        # fused vs unfused: same slope decisions, different fp32 summation orders only
+        assert float((a - c).abs().max()) <= 2e-5 * scale * max(1.0, math.sqrt(M / 4096.0)), \
+            (n, float((a - c).abs().max()), scale)
+        # vs fp64: an activation within rounding of the LeakyReLU kink may take the other slope -- isolated elements
+        # of dx, and O(|dA| |x|) per flipped element in the sums over the rows (dw, dgamma, dbeta)
+        bad = (a.double() - b).abs() > 5e-5 * scale
+        if n == "dx":
+            assert int(bad.sum()) <= 4 + a.numel() // 100000, (n, int(bad.sum()))
+        else:
+            assert float((a.double() - b).abs().max()) <= 1e-3 * scale, (n, float((a.double() - b).abs().max()), scale)
+    close(bn_b.running_mean, bn_a.running_mean.float(), 1e-5, "running_mean")
+    close(bn_b.running_var, bn_a.running_var.float(), 1e-5, "running_var")

@@ -86,7 +86,7 @@ def main():
         res.append(dict(dW=True, M=M, K=K, N=N, rel_err=float((out.double() - ref).abs().max() / ref.abs().max())))
         print(res[-1], flush=True)
     if not quick:
-        for (M, K, N) in [(8_000_000, 128, 128), (1_280_000, 64, 128), (1_000_000, 512, 512)]:
+        for (M, K, N) in [(8_000_000, 128, 128), (1_280_000, 64, 128), (1_280_000, 64, 64), (1_600_000, 128, 128), (1_000_000, 512, 512)]:
             x = torch.randn(M, K, device="cuda")
             dz = torch.randn(M, N, device="cuda")
             ms = timeit(lambda: ops._tc_gemm(dz, x, 2, K))
