@@ -145,6 +145,8 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float(r);
 }
 
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
 // ---- weight preparation: W [N, K] (or its transpose) -> hi / lo, rows zero-padded to a multiple of 128 ----
 // transpose = 0: Wp[n, k] = W[n * ldw + k]      (forward: output column n, reduction k)
 // transpose = 1: Wp[n, k] = W[k * ldw + n]      (dX: output column n = input channel, reduction k = out channel)
@@ -171,7 +173,19 @@ struct RowsParams {
   int64_t M;
   int n_out, n_tiles, k_blocks, ldo;
   int64_t m_tiles;
+  int rep_cols;          // 128, or 32 / 64: narrow layer with the weight replicated over the TMEM lane quadrants (below)
 };
+
+// Narrow layers (n_out <= 64, weight in tensor memory): with lane = output column, a 32-wide layer would leave the
+// whole epilogue of a 128-row tile (4 tcgen05.ld, 128 row stores, the statistics) to the ONE warp that may read
+// lane quadrant 0 -- ~1.2 us per tile, the kernel's pace.  The M = 128 MMA computes all 128 lanes anyway, so the
+// weight rows are REPLICATED over the quadrants (lane l holds output column l % rep_cols) and quadrant j's warp
+// stores rows [rep_cols * j', ...) of the tile: same tensor work, the epilogue spread over 4 (2) warps.
+static inline int rows_rep_cols(int64_t n_out, int64_t k_red) {
+  const bool resident = n_out <= kTile && k_red <= 4 * kBK;
+  if (!resident || n_out > 64) return kTile;
+  return n_out <= 32 ? 32 : 64;
+}
 
 // WTMEM = true : K <= 128 and one column tile: the weight (hi, lo) lives in TENSOR MEMORY for the whole kernel
 //                (tcgen05.mma with the A operand from TMEM): shared memory only carries the X stages (6 x 32 KB)
@@ -300,11 +314,12 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < kTileBytes / 16 / kSplitThreads; ++i) {
           const int e = i * kSplitThreads + tid;
+          // hi is the landed fp32 tile itself: kind::tf32 reads the upper 19 bits of each word (truncation), so
+          // lo = tf32(x - trunc(x)) completes the split exactly and the 16 KB hi write-back is saved
           const float4 v = hi[e];
-          float4 h, l;
-          h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-          l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-          hi[e] = h;
+          float4 l;
+          l.x = tf32_rna(v.x - tf32_trunc(v.x)); l.y = tf32_rna(v.y - tf32_trunc(v.y));
+          l.z = tf32_rna(v.z - tf32_trunc(v.z)); l.w = tf32_rna(v.w - tf32_trunc(v.w));
           lo[e] = l;
         }
         fence_proxy_async();                             // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -316,12 +331,15 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   } else {
     // ===================== epilogue: TMEM -> registers -> coalesced global stores =====================
     const int q = warp & 3;                              // TMEM lane quadrant this warp may access
-    const int col = q * 32 + lane;                       // output column within the tile (TMEM lane)
+    const int col = q * 32 + lane;                       // TMEM lane
+    const int rep = WTMEM ? p.rep_cols : kTile;
+    const int part = col / rep;                          // which slice of the tile's rows this lane stores
+    const int src_col = col - part * rep;                // output column within the tile
     if (WTMEM) {
-      // the weight tile into tensor memory: lane = output column, TMEM column = k (row-major prep buffers
-      // [128, K], zero padded rows); 32 columns per tcgen05.st
-      const float* whi = p.w_hi + (int64_t)col * p.k_red;
-      const float* wlo = p.w_lo + (int64_t)col * p.k_red;
+      // the weight tile into tensor memory: lane = output column (mod rep_cols), TMEM column = k (row-major prep
+      // buffers [128, K], zero padded rows); 32 columns per tcgen05.st
+      const float* whi = p.w_hi + (int64_t)src_col * p.k_red;
+      const float* wlo = p.w_lo + (int64_t)src_col * p.k_red;
       for (int c0 = 0; c0 < KB * kBK; c0 += 32) {
         uint32_t rh[32], rl[32];
 #pragma unroll
@@ -347,15 +365,15 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
       const int64_t mt = t / p.n_tiles;
       const int nt = (int)(t - mt * p.n_tiles);
-      const int n = nt * kTile + col;
+      const int n = nt * kTile + src_col;
       const bool col_ok = n < p.n_out;
-      const bool warp_ok = nt * kTile + q * 32 < p.n_out;
+      const bool warp_ok = rep < kTile || nt * kTile + q * 32 < p.n_out;
       mbar_wait(tmem_full(acc), aph);
       tc_fence_after();
       if (warp_ok) {
         const int64_t row0 = mt * kTile;
 #pragma unroll 1
-        for (int c0 = 0; c0 < kTile; c0 += 32) {
+        for (int c0 = part * rep; c0 < (part + 1) * rep; c0 += 32) {
           if (row0 + c0 >= p.M) break;
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTile + c0), r);
@@ -556,11 +574,12 @@ tc_dw_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__
         float4* lo = reinterpret_cast<float4*>(st + x_lo_off);
         for (int i = 0; i < b_groups * (kGroupBytes / 16) / kSplitThreads; ++i) {
           const int e = i * kSplitThreads + tid;
+          // hi is the landed fp32 tile itself: kind::tf32 reads the upper 19 bits of each word (truncation), so
+          // lo = tf32(x - trunc(x)) completes the split exactly and the 16 KB hi write-back is saved
           const float4 v = hi[e];
-          float4 h, l;
-          h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-          l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-          hi[e] = h;
+          float4 l;
+          l.x = tf32_rna(v.x - tf32_trunc(v.x)); l.y = tf32_rna(v.y - tf32_trunc(v.y));
+          l.z = tf32_rna(v.z - tf32_trunc(v.z)); l.w = tf32_rna(v.w - tf32_trunc(v.w));
           lo[e] = l;
         }
       }
@@ -617,21 +636,29 @@ dw_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int
 // One warp per column; lanes stride over the CTAs in a fixed order, fp64 combine:
 //   sum_b = s_b + n_b sh_b,   sumsq_b = q_b + 2 sh_b s_b + n_b sh_b^2,   n_b = rows CTA b processed.
 __global__ void __launch_bounds__(128)
-bn_stats_finalize_kernel(const float* __restrict__ col_stats, int ctas, int64_t M, int64_t m_tiles, int C,
+bn_stats_finalize_kernel(const float* __restrict__ col_stats, int ctas, int64_t M, int64_t m_tiles, int C, int rep,
                          float eps, float momentum, float* __restrict__ mean, float* __restrict__ invstd,
                          float* __restrict__ running_mean, float* __restrict__ running_var) {
   const int lane = threadIdx.x & 31;
   const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
   double S = 0.0, Q = 0.0;
-  for (int b = lane; b < ctas; b += 32) {
+  const int parts = kTile / rep;                       // slot part * rep + c: column c over rows [part * rep, + rep) of each tile
+  const int64_t rem = M - (m_tiles - 1) * kTile;       // rows of the globally last tile
+  for (int e = lane; e < ctas * parts; e += 32) {
+    const int b = e / parts, part = e - b * parts;
     // tiles b, b + ctas, ...: all full except possibly the globally last one
     const int64_t nt = b < m_tiles ? (m_tiles - 1 - b) / ctas + 1 : 0;
-    int64_t nb = nt * kTile;
-    if (nt > 0 && b + (nt - 1) * ctas == m_tiles - 1) nb -= m_tiles * kTile - M;
-    const double s = (double)col_stats[((int64_t)b * 3 + 0) * kTile + c];
-    const double q = (double)col_stats[((int64_t)b * 3 + 1) * kTile + c];
-    const double sh = (double)col_stats[((int64_t)b * 3 + 2) * kTile + c];
+    int64_t nb = nt * rep;
+    if (nt > 0 && b + (nt - 1) * ctas == m_tiles - 1) {
+      int64_t last = rem - (int64_t)part * rep;
+      last = last < 0 ? 0 : (last > rep ? rep : last);
+      nb += last - rep;
+    }
+    const int slot = part * rep + c;
+    const double s = (double)col_stats[((int64_t)b * 3 + 0) * kTile + slot];
+    const double q = (double)col_stats[((int64_t)b * 3 + 1) * kTile + slot];
+    const double sh = (double)col_stats[((int64_t)b * 3 + 2) * kTile + slot];
     S += s + (double)nb * sh;
     Q += q + 2.0 * sh * s + (double)nb * sh * sh;
   }
@@ -732,6 +759,7 @@ extern "C" int dva_tc_rows_gemm(const float* X, const float* W, float* D, int64_
   p.out = D; p.col_stats = col_stats; p.M = M; p.n_out = (int)n_out; p.n_tiles = n_pad / tc::kTile;
   p.k_blocks = (int)((k_red + tc::kBK - 1) / tc::kBK); p.ldo = (int)ldo; p.m_tiles = (M + tc::kTile - 1) / tc::kTile;
   const bool resident = p.n_tiles == 1 && p.k_blocks <= 4;
+  p.rep_cols = tc::rows_rep_cols(n_out, k_red);
   if (col_stats && p.n_tiles != 1) return fail(DVA_EUNSUPPORTED, "tc_rows_gemm: column statistics need n_out <= 128");
   const int64_t tiles = p.m_tiles * p.n_tiles;
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
@@ -841,6 +869,7 @@ extern "C" int dva_linear_bnstats_fwd(const float* X, const float* W, float* D, 
   int rc = dva_tc_rows_gemm(X, W, D, M, n_out, k_red, k_red, k_red, n_out, 0, stats, &ctas, workspace, wbytes, stream);
   if (rc) return rc;
   tc::bn_stats_finalize_kernel<<<(int)((n_out + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
-      stats, ctas, M, (M + tc::kTile - 1) / tc::kTile, (int)n_out, eps, momentum, mean, invstd, running_mean, running_var);
+      stats, ctas, M, (M + tc::kTile - 1) / tc::kTile, (int)n_out, tc::rows_rep_cols(n_out, k_red), eps, momentum, mean,
+      invstd, running_mean, running_var);
   return check_launch("bn_stats_finalize");
 }
