@@ -62,6 +62,28 @@ def test_knobs_and_workspace_queries_validate_arguments():
     assert rc == _lib.DVA_EUNSUPPORTED
 
 
+def test_mlp_layer_entry_points_validate_shapes():
+    """Host-side shape rules of the fused layer entry points (no launch)."""
+    lib = _lib.load()
+    # fused narrow-layer backward: N <= 32 outputs, K <= 64 inputs, both multiples of 4
+    assert lib.dva_mlp_layer_bwd_supported(1000, 32, 32) == 1
+    assert lib.dva_mlp_layer_bwd_supported(1000, 32, 8) == 1
+    assert lib.dva_mlp_layer_bwd_supported(1000, 16, 64) == 1
+    for shape in ((1000, 64, 32), (1000, 32, 128), (1000, 30, 32), (1000, 32, 33), (0, 32, 32)):
+        assert lib.dva_mlp_layer_bwd_supported(*shape) == 0, shape
+        assert lib.dva_mlp_layer_bwd_workspace_bytes(*shape) == 0
+    assert lib.dva_mlp_layer_bwd_workspace_bytes(1000, 32, 32) >= 32 * 32 * 4
+    rc = lib.dva_mlp_layer_bwd(*([None] * 11), 1000, 64, 32, 0.2, None, 0, None)
+    assert rc == _lib.DVA_EUNSUPPORTED
+    rc = lib.dva_mlp_layer_bwd(*([None] * 11), 1000, 32, 32, 0.2, None, 0, None)
+    assert rc == _lib.DVA_EINVAL and b"mlp_layer_bwd" in lib.dva_last_error()
+    # GEMM with the BatchNorm statistics in its epilogue: one column tile (N <= 128), TMA rows (multiples of 4)
+    assert lib.dva_linear_bnstats_supported(1000, 128, 128) == 1
+    assert lib.dva_linear_bnstats_supported(1000, 256, 128) == 0
+    assert lib.dva_linear_bnstats_supported(1000, 128, 130) == 0
+    assert lib.dva_linear_bnstats_workspace_bytes(128, 128) > 148 * 3 * 128 * 4
+
+
 def test_no_cpu_fallback():
     import torch
     from deepviewagg_b200 import ops
