@@ -6,8 +6,8 @@
 //                        dX = dz . W  and  dW += dz^T . x  from the same tile            reads dA, z, x; writes dX
 // Before: BN-apply (2 R + 1 W), dX GEMM (1 R + 1 W), dW GEMM (2 R) = 5 R + 2 W passes and three launches after
 // the reduction; now 3 R + 1 W and one launch.  3xTF32 split operands on mma.sync.m16n8k8 (fp32-grade accuracy,
-// the arithmetic of skinny_gemm.cu): 2 * 2 * N * K * 3 tensor flops per row is ~150 us at 1.28 M x 32 x 32 on the
-// legacy-MMA rate of this part (~105 TFLOP/s) against 100 us of HBM time -- the tensor pipe, not HBM, paces it.
+// the arithmetic of skinny_gemm.cu).  Measured at 1.28 M x 32 x 32: 0.106 ms against 0.100 ms of HBM time (the first
+// version, with integer divisions by the run-time row width in the copy loops, was issue-bound at 0.137 ms).
 //
 // A WARP is its own pipeline: 16-row tiles (dA, z, x) double-buffered with cp.async in the warp's private shared
 // memory, no CTA-wide barrier inside the loop; the dW accumulators (N x K, 32 .. 64 registers per lane) live in
@@ -93,20 +93,28 @@ mlp_layer_bwd_kernel(const MlParams p) {
     c_is[j] = coef[3 * kMlN + cc + j]; c_k0[j] = coef[4 * kMlN + cc + j]; c_k1[j] = coef[5 * kMlN + cc + j];
   }
 
+  // fixed lane -> (row, 16-byte chunk) map, no divisions: lane owns chunk c4 = lane % 8 (and c4 + 8 of x when
+  // K > 32) of rows lane / 8 + 4 i
+  const int c4 = lane & 7, rr = lane >> 3;
+  constexpr int XH = (NT + 3) / 4;                   // 8-chunk column blocks of x: 2 for K > 32
   auto load = [&](float* buf, int64_t t) {
     const int64_t row0 = t * kMlRows;
     const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(buf);
-    for (int e = lane; e < kMlRows * nc4; e += 32) {
-      const int r = e / nc4, c = (e - r * nc4) << 2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = rr + 4 * i;
       const bool in = row0 + r < p.M;
-      const int64_t off = in ? (row0 + r) * N + c : 0;
-      ml_cp16(s0 + (uint32_t)(r * kMlNP + c) * 4, p.dA + off, in);
-      ml_cp16(s0 + (uint32_t)(kMlRows * kMlNP + r * kMlNP + c) * 4, p.Z + off, in);
-    }
-    for (int e = lane; e < kMlRows * kc4; e += 32) {
-      const int r = e / kc4, c = (e - r * kc4) << 2;
-      const bool in = row0 + r < p.M;
-      ml_cp16(s0 + (uint32_t)(2 * kMlRows * kMlNP + r * KP + c) * 4, p.X + (in ? (row0 + r) * K + c : 0), in);
+      if (c4 < nc4) {
+        const int64_t off = in ? (row0 + r) * N + c4 * 4 : 0;
+        ml_cp16(s0 + (uint32_t)(r * kMlNP + c4 * 4) * 4, p.dA + off, in);
+        ml_cp16(s0 + (uint32_t)(kMlRows * kMlNP + r * kMlNP + c4 * 4) * 4, p.Z + off, in);
+      }
+#pragma unroll
+      for (int h = 0; h < XH; ++h) {
+        const int cx = c4 + 8 * h;
+        if (cx < kc4)
+          ml_cp16(s0 + (uint32_t)(2 * kMlRows * kMlNP + r * KP + cx * 4) * 4, p.X + (in ? (row0 + r) * K + cx * 4 : 0), in);
+      }
     }
   };
 
@@ -224,10 +232,15 @@ mlp_layer_bwd_kernel(const MlParams p) {
         *reinterpret_cast<float2*>(o + 8 * KP) = make_float2(acc_x[j][2], acc_x[j][3]);
       }
       __syncwarp();
-      for (int e = lane; e < kMlRows * kc4; e += 32) {
-        const int r = e / kc4, c = (e - r * kc4) << 2;
-        if (row0 + r < p.M)
-          *reinterpret_cast<float4*>(p.dX + (row0 + r) * K + c) = *reinterpret_cast<const float4*>(xS + r * KP + c);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = rr + 4 * i;
+#pragma unroll
+        for (int h = 0; h < XH; ++h) {
+          const int cx = c4 + 8 * h;
+          if (cx < kc4 && row0 + r < p.M)
+            *reinterpret_cast<float4*>(p.dX + (row0 + r) * K + cx * 4) = *reinterpret_cast<const float4*>(xS + r * KP + cx * 4);
+        }
       }
     }
     __syncwarp();                                    // the stage may be refilled two iterations from now

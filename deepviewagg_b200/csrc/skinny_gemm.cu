@@ -422,11 +422,20 @@ skinny_dw_mma_kernel(const float* __restrict__ A, const float* __restrict__ B, f
     const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(buf), b0 = a0 + kSkDwRows * NP * 4;
     if (avec) {
       const int c4 = N >> 2;
-      for (int e = threadIdx.x; e < kSkDwRows * c4; e += blockDim.x) {
-        const int r = e / c4, c = (e - r * c4) << 2;
-        const bool in = row0 + r < M;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a0 + (uint32_t)(r * NP + c) * 4),
-                     "l"(A + (in ? (row0 + r) * N + c : 0)), "r"(in ? 16 : 0) : "memory");
+      if ((int)blockDim.x % c4 == 0) {               // the usual widths: a thread keeps its chunk, rows advance by a constant (no division in the loop)
+        const int c = ((int)threadIdx.x % c4) << 2, rstep = (int)blockDim.x / c4;
+        for (int r = threadIdx.x / c4; r < kSkDwRows; r += rstep) {
+          const bool in = row0 + r < M;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a0 + (uint32_t)(r * NP + c) * 4),
+                       "l"(A + (in ? (row0 + r) * N + c : 0)), "r"(in ? 16 : 0) : "memory");
+        }
+      } else {
+        for (int e = threadIdx.x; e < kSkDwRows * c4; e += blockDim.x) {
+          const int r = e / c4, c = (e - r * c4) << 2;
+          const bool in = row0 + r < M;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a0 + (uint32_t)(r * NP + c) * 4),
+                       "l"(A + (in ? (row0 + r) * N + c : 0)), "r"(in ? 16 : 0) : "memory");
+        }
       }
     } else {
       for (int e = threadIdx.x; e < kSkDwRows * N; e += blockDim.x) {
@@ -437,11 +446,20 @@ skinny_dw_mma_kernel(const float* __restrict__ A, const float* __restrict__ B, f
     float* bb = buf + kSkDwRows * NP;
     if (bvec) {
       const int c4 = kcols >> 2;
-      for (int e = threadIdx.x; e < kSkDwRows * c4; e += blockDim.x) {
-        const int r = e / c4, c = (e - r * c4) << 2;
-        const bool in = row0 + r < M;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(b0 + (uint32_t)(r * KP + c) * 4),
-                     "l"(B + (in ? (row0 + r) * K + kofs + c : 0)), "r"(in ? 16 : 0) : "memory");
+      if ((int)blockDim.x % c4 == 0) {
+        const int c = ((int)threadIdx.x % c4) << 2, rstep = (int)blockDim.x / c4;
+        for (int r = threadIdx.x / c4; r < kSkDwRows; r += rstep) {
+          const bool in = row0 + r < M;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(b0 + (uint32_t)(r * KP + c) * 4),
+                       "l"(B + (in ? (row0 + r) * K + kofs + c : 0)), "r"(in ? 16 : 0) : "memory");
+        }
+      } else {
+        for (int e = threadIdx.x; e < kSkDwRows * c4; e += blockDim.x) {
+          const int r = e / c4, c = (e - r * c4) << 2;
+          const bool in = row0 + r < M;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(b0 + (uint32_t)(r * KP + c) * 4),
+                       "l"(B + (in ? (row0 + r) * K + kofs + c : 0)), "r"(in ? 16 : 0) : "memory");
+        }
       }
     } else {
       for (int e = threadIdx.x; e < kSkDwRows * kcols; e += blockDim.x) {

@@ -828,9 +828,9 @@ class _MLPLayer(torch.autograd.Function):
         return dx, (dw.to(wdt) if ctx.needs_input_grad[1] else None), gw, gb, None, None, None, None, None
 
 
-# The fused backward runs on the legacy mma.sync pipe, which it saturates (5 clocks per m16n8k8 per SM): 137 us at
-# 1.28 M x 32 x 32 against 260 - 340 us for the three kernels it replaces, but no faster than them at K = 64
-# (329 against 294 us), where dX rides the tcgen05 kernel -> layers with K <= 32 only.
+# The fused backward (3xTF32 on mma.sync) takes 0.106 ms at 1.28 M x 32 x 32 (its HBM floor: 0.100) against
+# 0.26 - 0.34 ms for the three kernels it replaces, but is no faster than them at K = 64 (0.33 against 0.29 ms),
+# where dX rides the tcgen05 kernel -> layers with K <= 32 only.
 _MLP_LAYER_FUSED = {"on": os.environ.get("DVA_MLP_LAYER_FUSED", "1") != "0", "max_k": 32}
 
 

@@ -13,3 +13,6 @@ print("roofline", d["roofline"]["frac"], "e2e", d["e2e"]["value"], "cpu", d["cpu
 rd=d["roofline_detail"]; print("fwd", rd["fwd"]["frac"], "both", rd["fwd_plus_bwd"]["frac"])
 print("variant_b", rd.get("variant_b",{}).get("step_frac")); print("modules", {k:v.get("ms_per_step") for k,v in rd.get("modules",{}).items() if isinstance(v,dict)})
 PY
+timeout -s KILL 200 python tools/bench_layer.py --out gpurun_out/r2_layer.json 2>&1 | cut -c1-330
+timeout -s KILL 200 python tools/profile_module.py 160000 8 64 --no-mod > gpurun_out/r2_module_s3dis_profile.txt 2>&1; head -1 gpurun_out/r2_module_s3dis_profile.txt
+timeout -s KILL 200 python tools/profile_module.py 80000 20 128 --no-mod > gpurun_out/r2_module_kitti_profile.txt 2>&1; head -1 gpurun_out/r2_module_kitti_profile.txt
