@@ -828,7 +828,7 @@ class _MLPLayer(torch.autograd.Function):
         return dx, (dw.to(wdt) if ctx.needs_input_grad[1] else None), gw, gb, None, None, None, None, None
 
 
-# The fused backward (3xTF32 on mma.sync) takes 0.106 ms at 1.28 M x 32 x 32 (its HBM floor: 0.100) against
+# The fused backward (3xTF32 on mma.sync) takes 0.106 ms in a step at 1.28 M x 32 x 32 (HBM time: 0.100) against
 # 0.26 - 0.34 ms for the three kernels it replaces, but is no faster than them at K = 64 (0.33 against 0.29 ms),
 # where dX rides the tcgen05 kernel -> layers with K <= 32 only.
 _MLP_LAYER_FUSED = {"on": os.environ.get("DVA_MLP_LAYER_FUSED", "1") != "0", "max_k": 32}
